@@ -1,0 +1,73 @@
+// internal.h — types shared by the host side (host.cu) and the kernels (kernels.cu) of libb200ddp.so.
+// Nothing here is part of the C ABI (include/b200ddp.h is).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/b200ddp.h"
+
+namespace b200ddp {
+
+constexpr int kMaxWorld = B200DDP_MAX_WORLD;
+// One flag slot per (CTA index, source rank); grids of collective kernels are capped to this many CTAs.
+constexpr int kMaxBlocks = 512;
+// Tensors one multi-tensor launch can address (its table travels in the kernel-parameter space, so a
+// launch needs no device-side table memory and no H2D copy; see kernels.cu: TensorTable).
+constexpr int kMaxTableTensors = 160;
+// Largest bucket the single-launch fused path takes.
+constexpr uint64_t kFusedMaxBytes = 256u << 10;
+
+// Layout of the per-rank signal region that precedes the bucket arena inside the shared allocation.
+//   [0, kFlagBytes)              uint32 flag[kMaxBlocks][kMaxWorld]   written by peers, polled locally
+//   [kFlagBytes, +kEpochBytes)   uint32 epoch[kMaxBlocks]             local, per-CTA barrier generation
+constexpr uint64_t kFlagBytes = uint64_t(kMaxBlocks) * kMaxWorld * 4;
+constexpr uint64_t kEpochBytes = uint64_t(kMaxBlocks) * 4;
+constexpr uint64_t kSignalBytes = 2u << 20;  // one 2 MiB page: keeps the arena 2 MiB aligned
+static_assert(kFlagBytes + kEpochBytes <= kSignalBytes, "signal region too small");
+
+// Base addresses of every rank's shared allocation as mapped into THIS process.
+struct PeerTable {
+  uint64_t base[kMaxWorld];  // signal region at base, arena at base + kSignalBytes
+};
+
+// Per-launch control block.
+struct Ctl {
+  uint32_t* err;        // mapped host word: set to non-zero by a kernel that timed out on a peer
+  uint64_t timeout_ns;  // in-kernel barrier timeout
+  int rank;
+  int world;
+};
+
+// Multi-tensor table, passed BY VALUE as a kernel parameter (<= 4 KiB with the other arguments).
+// Tensor i occupies bucket vectors [off_vec[i], off_vec[i+1]) (16-byte units from the bucket start) and
+// holds len_el[i] elements starting at ptr[i].  off_vec is ascending; off_vec[n] closes the last tensor.
+struct TensorTable {
+  uint64_t ptr[kMaxTableTensors];
+  uint64_t len_el[kMaxTableTensors];
+  uint32_t off_vec[kMaxTableTensors + 1];
+  int32_t n;
+};
+
+struct LaunchCfg {
+  int max_ctas;  // 0 = default
+};
+
+// kernels.cu — launch wrappers.  All return cudaError_t from the launch.
+cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_begin, uint32_t vec_end, int dtype,
+                           float scale, bool unflatten, cudaStream_t s);
+cudaError_t launch_oneshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
+                           int dtype, int max_ctas, cudaStream_t s);
+cudaError_t launch_twoshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
+                           int dtype, int max_ctas, cudaStream_t s);
+cudaError_t launch_twoshot_tma(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off,
+                               uint64_t nvec, int dtype, int max_ctas, cudaStream_t s);
+cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, uint64_t in_off, uint64_t out_off,
+                        uint64_t nvec, int dtype, int max_ctas, cudaStream_t s);
+cudaError_t launch_fused(const TensorTable& tt, const PeerTable& pt, const Ctl& ctl, uint64_t bucket_off,
+                         uint32_t nvec, int dtype, float scale, cudaStream_t s);
+cudaError_t launch_broadcast(const PeerTable& pt, const Ctl& ctl, uint64_t off, uint64_t nvec, int root,
+                             int max_ctas, cudaStream_t s);
+cudaError_t launch_barrier(const PeerTable& pt, const Ctl& ctl, cudaStream_t s);
+cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, cudaStream_t s);
+cudaError_t prepare_kernels();  // one-time function attributes (dynamic smem opt-in)
+
+}  // namespace b200ddp

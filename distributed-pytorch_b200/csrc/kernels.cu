@@ -1,0 +1,849 @@
+// kernels.cu — sm_100a kernels of the B200-native DDP gradient-bucket path.
+//
+// What each kernel replaces in the reference's dependency stack (torch c10d, see include/b200ddp.h):
+//   multi_tensor_copy_kernel  Reducer::mark_variable_ready_dense (flatten + 1/ws pre-scale, reducer.hpp:276)
+//                             and copy_bucket_to_grad (unflatten, reducer.hpp:330): one launch per bucket
+//                             instead of one D2D launch per parameter.
+//   oneshot/twoshot/tma/nvls  ProcessGroupNCCL::allreduce -> ncclAllReduce(SUM) (ProcessGroupNCCL.hpp:856):
+//                             the kernel itself issues the NVLink traffic on peer-mapped arenas.
+//   fused_bucket_kernel       all three steps of a small bucket in a single launch.
+//
+// Design notes
+//   * Everything is a stream of 16-byte vectors (LDG.128/STG.128, L1::no_allocate): the path is pure
+//     bandwidth (0.25 FLOP/B), no tensor cores.
+//   * Sums are accumulated in fp32 in RANK ORDER 0..ws-1 on exactly one owner per element (two-shot) or
+//     identically on every rank (one-shot), so all ranks end with bit-identical buckets and the fp32
+//     result is independent of algorithm and grid size (NVLS excepted: the switch picks the order).
+//   * Cross-GPU synchronisation is a per-CTA flag barrier on peer-mapped signal pads: CTA b of rank r
+//     stores a monotonically increasing epoch into slot [b][r] of every peer with st.release.sys and
+//     spins with ld.acquire.sys on its own pad.  The epoch lives in device memory (per CTA), so a
+//     launch carries no host-side generation counter and can be replayed from a CUDA graph.
+//     CTA b only ever depends on CTA b of the peers, so no grid-wide co-residency is needed.
+//   * Spins are bounded by %globaltimer; a timeout raises a flag in mapped host memory instead of
+//     hanging the GPU (a dead peer becomes a Python exception).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "internal.h"
+
+namespace b200ddp {
+namespace {
+
+constexpr int kNumSMs = 148;
+
+// ---------------------------------------------------------------------------------------------------
+// 16-byte global accesses
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_vec(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_vec(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_vec(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// element-type arithmetic on one 16-byte vector; accumulation always in fp32, never contracted
+// ---------------------------------------------------------------------------------------------------
+template <int DT>
+struct Vec;
+
+template <>
+struct Vec<B200DDP_F32> {
+  static constexpr int N = 4;      // elements per 16-byte vector
+  static constexpr int ESIZE = 4;  // bytes per element
+  static __device__ __forceinline__ void unpack(const uint4& x, float (&f)[N]) {
+    f[0] = __uint_as_float(x.x);
+    f[1] = __uint_as_float(x.y);
+    f[2] = __uint_as_float(x.z);
+    f[3] = __uint_as_float(x.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&f)[N]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+
+template <>
+struct Vec<B200DDP_BF16> {
+  static constexpr int N = 8;
+  static constexpr int ESIZE = 2;
+  static __device__ __forceinline__ void unpack(const uint4& x, float (&f)[N]) {
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&f)[N]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <>
+struct Vec<B200DDP_F16> {
+  static constexpr int N = 8;
+  static constexpr int ESIZE = 2;
+  static __device__ __forceinline__ void unpack(const uint4& x, float (&f)[N]) {
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 p = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = p.x;
+      f[2 * i + 1] = p.y;
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&f)[N]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// sum of WS vectors in index order 0..WS-1 (= rank order), fp32 accumulate, one rounding on pack
+template <int DT, int WS>
+__device__ __forceinline__ uint4 reduce_vecs(const uint4 (&x)[WS]) {
+  float acc[Vec<DT>::N];
+  Vec<DT>::unpack(x[0], acc);
+#pragma unroll
+  for (int q = 1; q < WS; ++q) {
+    float f[Vec<DT>::N];
+    Vec<DT>::unpack(x[q], f);
+#pragma unroll
+    for (int i = 0; i < Vec<DT>::N; ++i) acc[i] = __fadd_rn(acc[i], f[i]);
+  }
+  return Vec<DT>::pack(acc);
+}
+
+template <int DT>
+__device__ __forceinline__ uint4 scale_vec(const uint4& x, float scale) {
+  float f[Vec<DT>::N];
+  Vec<DT>::unpack(x, f);
+#pragma unroll
+  for (int i = 0; i < Vec<DT>::N; ++i) f[i] = __fmul_rn(f[i], scale);
+  return Vec<DT>::pack(f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cross-GPU per-CTA barrier on the signal pads
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ uint32_t* flag_slot(uint64_t base, int block, int src) {
+  return reinterpret_cast<uint32_t*>(base) + (block * kMaxWorld + src);
+}
+__device__ __forceinline__ uint32_t* epoch_slot(uint64_t base, int block) {
+  return reinterpret_cast<uint32_t*>(base + kFlagBytes) + block;
+}
+__device__ __forceinline__ uint32_t read_epoch(const PeerTable& pt, const Ctl& ctl) {
+  return *reinterpret_cast<volatile uint32_t*>(epoch_slot(pt.base[ctl.rank], blockIdx.x));
+}
+__device__ __forceinline__ void write_epoch(const PeerTable& pt, const Ctl& ctl, uint32_t e) {
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(epoch_slot(pt.base[ctl.rank], blockIdx.x)) = e;
+}
+
+// Every thread of the CTA calls this.  On return all CTAs with this blockIdx on all ranks have arrived
+// with `target`, and their prior writes (local and peer) are visible to this CTA.
+__device__ __forceinline__ void cta_barrier(const PeerTable& pt, const Ctl& ctl, int ws, uint32_t target) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < ws) {
+    const int q = threadIdx.x;
+    st_release_sys(flag_slot(pt.base[q], blockIdx.x, ctl.rank), target);
+    const uint32_t* mine = flag_slot(pt.base[ctl.rank], blockIdx.x, q);
+    const uint64_t t0 = globaltimer_ns();
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - target) < 0) {
+      if (globaltimer_ns() - t0 > ctl.timeout_ns) {
+        *reinterpret_cast<volatile uint32_t*>(ctl.err) = 1u + static_cast<uint32_t>(q);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint64_t arena_of(const PeerTable& pt, int q) { return pt.base[q] + kSignalBytes; }
+
+// ---------------------------------------------------------------------------------------------------
+// multi-tensor flatten(+scale) / unflatten
+// ---------------------------------------------------------------------------------------------------
+struct SmemTable {
+  uint64_t ptr[kMaxTableTensors];
+  uint64_t len[kMaxTableTensors];
+  uint32_t off[kMaxTableTensors + 1];
+};
+
+__device__ __forceinline__ void load_table(SmemTable& s, const TensorTable& tt) {
+  const int n = tt.n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s.ptr[i] = tt.ptr[i];
+    s.len[i] = tt.len_el[i];
+  }
+  for (int i = threadIdx.x; i <= n; i += blockDim.x) s.off[i] = tt.off_vec[i];
+  __syncthreads();
+}
+
+// largest t in [lo, hi] with off[t] <= v   (requires off[lo] <= v)
+__device__ __forceinline__ int locate(const uint32_t* off, int lo, int hi, uint32_t v) {
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (off[mid] <= v)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+// read bucket-vector v of tensor t from the tensor's own storage (zero padded past its end)
+template <int DT>
+__device__ __forceinline__ uint4 gather_vec(const SmemTable& s, int t, uint32_t v) {
+  constexpr int N = Vec<DT>::N;
+  const uint64_t e0 = static_cast<uint64_t>(v - s.off[t]) * N;
+  const uint64_t len = s.len[t];
+  const uint64_t addr = s.ptr[t] + e0 * Vec<DT>::ESIZE;
+  if (e0 + N <= len && (addr & 15) == 0) return ld_vec(reinterpret_cast<const void*>(addr));
+  uint4 r = make_uint4(0, 0, 0, 0);
+  if (e0 >= len) return r;
+  const int valid = static_cast<int>(min(static_cast<uint64_t>(N), len - e0));
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (Vec<DT>::ESIZE == 4) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(addr);
+    for (int i = 0; i < valid; ++i) w[i] = p[i];
+  } else {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(addr);
+    for (int i = 0; i < valid; ++i) w[i >> 1] |= static_cast<uint32_t>(p[i]) << (16 * (i & 1));
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// write bucket-vector v of tensor t to the tensor's own storage (only its valid elements)
+template <int DT>
+__device__ __forceinline__ void scatter_vec(const SmemTable& s, int t, uint32_t v, const uint4& x) {
+  constexpr int N = Vec<DT>::N;
+  const uint64_t e0 = static_cast<uint64_t>(v - s.off[t]) * N;
+  const uint64_t len = s.len[t];
+  if (e0 >= len) return;
+  const uint64_t addr = s.ptr[t] + e0 * Vec<DT>::ESIZE;
+  if (e0 + N <= len && (addr & 15) == 0) {
+    st_vec(reinterpret_cast<void*>(addr), x);
+    return;
+  }
+  const int valid = static_cast<int>(min(static_cast<uint64_t>(N), len - e0));
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+  if (Vec<DT>::ESIZE == 4) {
+    uint32_t* p = reinterpret_cast<uint32_t*>(addr);
+    for (int i = 0; i < valid; ++i) p[i] = w[i];
+  } else {
+    uint16_t* p = reinterpret_cast<uint16_t*>(addr);
+    for (int i = 0; i < valid; ++i) p[i] = static_cast<uint16_t>(w[i >> 1] >> (16 * (i & 1)));
+  }
+}
+
+constexpr int kCopyThreads = 512;
+constexpr int kCopyUnroll = 4;
+constexpr uint32_t kCopyTile = kCopyThreads * kCopyUnroll;  // vectors per tile = 32 KiB
+
+// One launch moves bucket vectors [vec_begin, vec_end) (all inside the tensors of `tt`).
+// HBM-bound: reads S + writes S bytes for S bytes of gradients.
+template <int DT, bool UNFLATTEN>
+__global__ void __launch_bounds__(kCopyThreads)
+multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* __restrict__ bucket,
+                         uint32_t vec_begin, uint32_t vec_end, float scale) {
+  __shared__ SmemTable s;
+  load_table(s, tt);
+  const int n = tt.n;
+  const uint32_t ntiles = (vec_end - vec_begin + kCopyTile - 1) / kCopyTile;
+  uint4* bvec = reinterpret_cast<uint4*>(bucket);
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t v0 = vec_begin + tile * kCopyTile;
+    const uint32_t v1 = min(v0 + kCopyTile, vec_end);
+    const int t_lo = locate(s.off, 0, n - 1, v0);
+    const int t_hi = locate(s.off, t_lo, n - 1, v1 - 1);
+    const uint64_t first = static_cast<uint64_t>(v0 - s.off[t_lo]);
+    const bool fast = (t_lo == t_hi) && ((s.ptr[t_lo] & 15) == 0) &&
+                      (static_cast<uint64_t>(v1 - s.off[t_lo]) * Vec<DT>::N <= s.len[t_lo]);
+    if (fast) {
+      // whole tile inside one aligned tensor: straight vector copy, kCopyUnroll loads in flight/thread
+      uint4* tvec = reinterpret_cast<uint4*>(s.ptr[t_lo]) + first;
+      const uint32_t cnt = v1 - v0;
+      uint4 x[kCopyUnroll];
+#pragma unroll
+      for (int j = 0; j < kCopyUnroll; ++j) {
+        const uint32_t i = threadIdx.x + j * kCopyThreads;
+        if (i < cnt) x[j] = UNFLATTEN ? ld_vec(bvec + v0 + i) : ld_vec(tvec + i);
+      }
+#pragma unroll
+      for (int j = 0; j < kCopyUnroll; ++j) {
+        const uint32_t i = threadIdx.x + j * kCopyThreads;
+        if (i < cnt) {
+          if (UNFLATTEN)
+            st_vec(tvec + i, x[j]);
+          else
+            st_vec(bvec + v0 + i, scale_vec<DT>(x[j], scale));
+        }
+      }
+    } else {
+      // tile spans tensor boundaries (many small tensors), tails or unaligned storage
+#pragma unroll 1
+      for (uint32_t v = v0 + threadIdx.x; v < v1; v += kCopyThreads) {
+        const int t = locate(s.off, t_lo, t_hi, v);
+        if (UNFLATTEN)
+          scatter_vec<DT>(s, t, v, ld_vec(bvec + v));
+        else
+          st_vec(bvec + v, scale_vec<DT>(gather_vec<DT>(s, t, v), scale));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) local_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
+                                                         uint64_t nvec) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < nvec; i += uint64_t(gridDim.x) * blockDim.x)
+    st_vec(dst + i, ld_vec(src + i));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// one-shot allreduce: every rank reads the whole bucket from every peer (small buckets, latency bound)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kArThreads = 512;
+
+template <int DT, int WS>
+__global__ void __launch_bounds__(kArThreads)
+oneshot_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t in_off,
+               uint64_t out_off, uint64_t nvec) {
+  const uint32_t e = read_epoch(pt, ctl);
+  cta_barrier(pt, ctl, WS, e + 1);
+  const uint4* in[WS];
+#pragma unroll
+  for (int q = 0; q < WS; ++q) in[q] = reinterpret_cast<const uint4*>(arena_of(pt, q) + in_off);
+  uint4* out = reinterpret_cast<uint4*>(arena_of(pt, ctl.rank) + out_off);
+  for (uint64_t i = blockIdx.x * uint64_t(kArThreads) + threadIdx.x; i < nvec; i += uint64_t(gridDim.x) * kArThreads) {
+    uint4 x[WS];
+#pragma unroll
+    for (int q = 0; q < WS; ++q) x[q] = ld_vec(in[q] + i);
+    st_vec(out + i, reduce_vecs<DT, WS>(x));
+  }
+  cta_barrier(pt, ctl, WS, e + 2);
+  write_epoch(pt, ctl, e + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// two-shot allreduce, register path: rank r owns slice r; it loads that slice from all ws arenas with
+// LDG.128, reduces, and pushes the result into all ws arenas with STG.128 (reduce-scatter and
+// all-gather fused per vector; in-place safe because the owner is the only reader of its slice).
+// NVLink bytes per GPU and direction: 2 (ws-1)/ws S.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTwoShotUnroll = 2;
+
+template <int DT, int WS>
+__global__ void __launch_bounds__(kArThreads)
+twoshot_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t in_off,
+               uint64_t out_off, uint64_t nvec) {
+  const uint32_t e = read_epoch(pt, ctl);
+  cta_barrier(pt, ctl, WS, e + 1);
+  const uint64_t slice = (nvec + WS - 1) / WS;
+  const uint64_t begin = min(nvec, slice * ctl.rank);
+  const uint64_t end = min(nvec, begin + slice);
+  const uint4* in[WS];
+  uint4* out[WS];
+#pragma unroll
+  for (int q = 0; q < WS; ++q) {
+    in[q] = reinterpret_cast<const uint4*>(arena_of(pt, q) + in_off);
+    out[q] = reinterpret_cast<uint4*>(arena_of(pt, q) + out_off);
+  }
+  constexpr uint64_t kStep = uint64_t(kArThreads) * kTwoShotUnroll;
+  for (uint64_t i0 = begin + blockIdx.x * kStep + threadIdx.x; i0 < end; i0 += uint64_t(gridDim.x) * kStep) {
+    uint4 x[kTwoShotUnroll][WS];
+#pragma unroll
+    for (int u = 0; u < kTwoShotUnroll; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * kArThreads;
+      if (i < end) {
+#pragma unroll
+        for (int q = 0; q < WS; ++q) x[u][q] = ld_vec(in[q] + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kTwoShotUnroll; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * kArThreads;
+      if (i < end) {
+        const uint4 r = reduce_vecs<DT, WS>(x[u]);
+#pragma unroll
+        for (int q = 0; q < WS; ++q) st_vec(out[q] + i, r);
+      }
+    }
+  }
+  cta_barrier(pt, ctl, WS, e + 2);
+  write_epoch(pt, ctl, e + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// two-shot allreduce, TMA path: one elected producer thread streams 4 KiB pieces of the owned slice
+// from all ws arenas into a shared-memory ring with cp.async.bulk (UBLKCP) completing on mbarriers;
+// 8 consumer warps reduce from shared memory and push results to all arenas.  Bytes in flight per CTA
+// = 128 KiB independent of register count, so a few CTAs saturate NVLink and the backward keeps the SMs.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTmaChunkVec = 256;                       // vectors per arena per stage (4 KiB)
+constexpr int kTmaChunkBytes = kTmaChunkVec * 16;       //
+constexpr int kTmaConsumerWarps = 8;                    // 256 consumer threads = one vector each per stage
+constexpr int kTmaThreads = 32 + 32 * kTmaConsumerWarps;
+__host__ __device__ constexpr int tma_stages(int ws) { return 32 / ws; }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int DT, int WS>
+__global__ void __launch_bounds__(kTmaThreads)
+twoshot_tma_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t in_off,
+                   uint64_t out_off, uint64_t nvec) {
+  constexpr int STAGES = tma_stages(WS);
+  extern __shared__ __align__(128) unsigned char ring[];  // STAGES * WS * 4 KiB
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring));
+  const uint32_t full_s = static_cast<uint32_t>(__cvta_generic_to_shared(full_bar));
+  const uint32_t empty_s = static_cast<uint32_t>(__cvta_generic_to_shared(empty_bar));
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_s + 8 * i, 1);
+      mbar_init(empty_s + 8 * i, kTmaConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t e = read_epoch(pt, ctl);
+  cta_barrier(pt, ctl, WS, e + 1);  // also publishes the mbarrier inits (contains __syncthreads)
+
+  const uint64_t slice = (nvec + WS - 1) / WS;
+  const uint64_t begin = min(nvec, slice * ctl.rank);
+  const uint64_t end = min(nvec, begin + slice);
+  const uint64_t ntiles = (end - begin + kTmaChunkVec - 1) / kTmaChunkVec;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(empty_s + 8 * stage, phase ^ 1);
+        const uint64_t v0 = begin + t * kTmaChunkVec;
+        const uint32_t bytes = static_cast<uint32_t>(min(static_cast<uint64_t>(kTmaChunkVec), end - v0)) * 16;
+        mbar_expect_tx(full_s + 8 * stage, bytes * WS);
+#pragma unroll
+        for (int q = 0; q < WS; ++q)
+          bulk_g2s(ring_s + (stage * WS + q) * kTmaChunkBytes,
+                   reinterpret_cast<const void*>(arena_of(pt, q) + in_off + v0 * 16), bytes, full_s + 8 * stage);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int ctid = tid - 32;
+    uint4* out[WS];
+#pragma unroll
+    for (int q = 0; q < WS; ++q) out[q] = reinterpret_cast<uint4*>(arena_of(pt, q) + out_off);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      mbar_wait(full_s + 8 * stage, phase);
+      const uint64_t v0 = begin + t * kTmaChunkVec;
+      const uint32_t cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(kTmaChunkVec), end - v0));
+      if (ctid < cnt) {
+        uint4 x[WS];
+#pragma unroll
+        for (int q = 0; q < WS; ++q) x[q] = lds_vec(ring_s + (stage * WS + q) * kTmaChunkBytes + ctid * 16);
+        const uint4 r = reduce_vecs<DT, WS>(x);
+#pragma unroll
+        for (int q = 0; q < WS; ++q) st_vec(out[q] + v0 + ctid, r);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_s + 8 * stage);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  }
+  cta_barrier(pt, ctl, WS, e + 2);
+  write_epoch(pt, ctl, e + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NVLS allreduce: the owner of a slice pulls the switch-reduced sum with multimem.ld_reduce and
+// broadcasts it with multimem.st through the multicast mapping.  NVLink bytes per GPU and direction:
+// (1 + 1/ws) S instead of 2 (ws-1)/ws S.
+// ---------------------------------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ uint4 multimem_ld_reduce(const void* p);
+template <>
+__device__ __forceinline__ uint4 multimem_ld_reduce<B200DDP_F32>(const void* p) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+template <>
+__device__ __forceinline__ uint4 multimem_ld_reduce<B200DDP_BF16>(const void* p) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+template <>
+__device__ __forceinline__ uint4 multimem_ld_reduce<B200DDP_F16>(const void* p) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(void* p, const uint4& v) {
+  // the payload is opaque 16 bytes; .f32 only names the register class
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+constexpr int kNvlsUnroll = 4;
+
+template <int DT>
+__global__ void __launch_bounds__(kArThreads)
+nvls_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t mc_base, uint64_t in_off,
+            uint64_t out_off, uint64_t nvec) {
+  const int ws = ctl.world;
+  const uint32_t e = read_epoch(pt, ctl);
+  cta_barrier(pt, ctl, ws, e + 1);
+  const uint64_t slice = (nvec + ws - 1) / ws;
+  const uint64_t begin = min(nvec, slice * ctl.rank);
+  const uint64_t end = min(nvec, begin + slice);
+  const uint4* in = reinterpret_cast<const uint4*>(mc_base + kSignalBytes + in_off);
+  uint4* out = reinterpret_cast<uint4*>(mc_base + kSignalBytes + out_off);
+  constexpr uint64_t kStep = uint64_t(kArThreads) * kNvlsUnroll;
+  for (uint64_t i0 = begin + blockIdx.x * kStep + threadIdx.x; i0 < end; i0 += uint64_t(gridDim.x) * kStep) {
+    uint4 x[kNvlsUnroll];
+#pragma unroll
+    for (int u = 0; u < kNvlsUnroll; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * kArThreads;
+      if (i < end) x[u] = multimem_ld_reduce<DT>(in + i);
+    }
+#pragma unroll
+    for (int u = 0; u < kNvlsUnroll; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * kArThreads;
+      if (i < end) multimem_st(out + i, x[u]);
+    }
+  }
+  cta_barrier(pt, ctl, ws, e + 2);
+  write_epoch(pt, ctl, e + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused small bucket: flatten+scale -> one-shot allreduce -> unflatten in ONE launch.
+// CTA b owns bucket vectors [b*kFusedVecPerCta, ...): it gathers them from the gradients into its own
+// arena, meets CTA b of every peer, sums the same range of all arenas and scatters the result straight
+// back into the gradients from registers.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 256;
+constexpr uint32_t kFusedVecPerCta = 1024;
+
+template <int DT, int WS>
+__global__ void __launch_bounds__(kFusedThreads)
+fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ PeerTable pt,
+                    const __grid_constant__ Ctl ctl, uint64_t bucket_off, uint32_t nvec, float scale) {
+  __shared__ SmemTable s;
+  load_table(s, tt);
+  const int n = tt.n;
+  const uint32_t v_begin = blockIdx.x * kFusedVecPerCta;
+  const uint32_t v_end = min(nvec, v_begin + kFusedVecPerCta);
+  uint4* mine = reinterpret_cast<uint4*>(arena_of(pt, ctl.rank) + bucket_off);
+  if (WS == 1) {
+    for (uint32_t v = v_begin + threadIdx.x; v < v_end; v += kFusedThreads) {
+      const int t = locate(s.off, 0, n - 1, v);
+      const uint4 x = scale_vec<DT>(gather_vec<DT>(s, t, v), scale);
+      st_vec(mine + v, x);
+      scatter_vec<DT>(s, t, v, x);
+    }
+    return;
+  }
+  const uint32_t e = read_epoch(pt, ctl);
+  for (uint32_t v = v_begin + threadIdx.x; v < v_end; v += kFusedThreads) {
+    const int t = locate(s.off, 0, n - 1, v);
+    st_vec(mine + v, scale_vec<DT>(gather_vec<DT>(s, t, v), scale));
+  }
+  cta_barrier(pt, ctl, WS, e + 1);
+  const uint4* in[WS];
+#pragma unroll
+  for (int q = 0; q < WS; ++q) in[q] = reinterpret_cast<const uint4*>(arena_of(pt, q) + bucket_off);
+  for (uint32_t v = v_begin + threadIdx.x; v < v_end; v += kFusedThreads) {
+    uint4 x[WS];
+#pragma unroll
+    for (int q = 0; q < WS; ++q) x[q] = ld_vec(in[q] + v);
+    const int t = locate(s.off, 0, n - 1, v);
+    scatter_vec<DT>(s, t, v, reduce_vecs<DT, WS>(x));
+  }
+  cta_barrier(pt, ctl, WS, e + 2);
+  write_epoch(pt, ctl, e + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// broadcast by peer stores, and a bare barrier
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kArThreads)
+broadcast_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t off, uint64_t nvec,
+                 int root) {
+  const int ws = ctl.world;
+  const uint32_t e = read_epoch(pt, ctl);
+  cta_barrier(pt, ctl, ws, e + 1);
+  if (ctl.rank == root) {
+    const uint4* src = reinterpret_cast<const uint4*>(arena_of(pt, root) + off);
+    for (uint64_t i = blockIdx.x * uint64_t(kArThreads) + threadIdx.x; i < nvec;
+         i += uint64_t(gridDim.x) * kArThreads) {
+      const uint4 x = ld_vec(src + i);
+      for (int q = 0; q < ws; ++q)
+        if (q != root) st_vec(reinterpret_cast<uint4*>(arena_of(pt, q) + off) + i, x);
+    }
+  }
+  cta_barrier(pt, ctl, ws, e + 2);
+  write_epoch(pt, ctl, e + 2);
+}
+
+__global__ void __launch_bounds__(32) barrier_kernel(const __grid_constant__ PeerTable pt,
+                                                     const __grid_constant__ Ctl ctl) {
+  const uint32_t e = read_epoch(pt, ctl);
+  cta_barrier(pt, ctl, ctl.world, e + 1);
+  write_epoch(pt, ctl, e + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dispatch helpers
+// ---------------------------------------------------------------------------------------------------
+inline int clamp_grid(uint64_t want, int max_ctas, int dflt) {
+  int cap = max_ctas > 0 ? max_ctas : dflt;
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  if (want < 1) want = 1;
+  return static_cast<int>(want < static_cast<uint64_t>(cap) ? want : static_cast<uint64_t>(cap));
+}
+
+#define B200_DISPATCH_DT(dt, ...)                       \
+  switch (dt) {                                         \
+    case B200DDP_F32: {                                 \
+      constexpr int DT = B200DDP_F32;                   \
+      __VA_ARGS__;                                      \
+    } break;                                            \
+    case B200DDP_BF16: {                                \
+      constexpr int DT = B200DDP_BF16;                  \
+      __VA_ARGS__;                                      \
+    } break;                                            \
+    case B200DDP_F16: {                                 \
+      constexpr int DT = B200DDP_F16;                   \
+      __VA_ARGS__;                                      \
+    } break;                                            \
+    default:                                            \
+      return cudaErrorInvalidValue;                     \
+  }
+
+#define B200_WS_CASE(n, ...) \
+  case n: {                  \
+    constexpr int WS = n;    \
+    __VA_ARGS__;             \
+  } break;
+
+#define B200_DISPATCH_WS(ws, ...)   \
+  switch (ws) {                     \
+    B200_WS_CASE(2, __VA_ARGS__)    \
+    B200_WS_CASE(3, __VA_ARGS__)    \
+    B200_WS_CASE(4, __VA_ARGS__)    \
+    B200_WS_CASE(5, __VA_ARGS__)    \
+    B200_WS_CASE(6, __VA_ARGS__)    \
+    B200_WS_CASE(7, __VA_ARGS__)    \
+    B200_WS_CASE(8, __VA_ARGS__)    \
+    default:                        \
+      return cudaErrorInvalidValue; \
+  }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------------
+cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_begin, uint32_t vec_end, int dtype,
+                           float scale, bool unflatten, cudaStream_t s) {
+  if (vec_end <= vec_begin || tt.n <= 0) return cudaSuccess;
+  const uint32_t ntiles = (vec_end - vec_begin + kCopyTile - 1) / kCopyTile;
+  const int grid = static_cast<int>(ntiles < uint32_t(kNumSMs * 4) ? ntiles : uint32_t(kNumSMs * 4));
+  unsigned char* b = static_cast<unsigned char*>(bucket);
+  B200_DISPATCH_DT(dtype, {
+    if (unflatten)
+      multi_tensor_copy_kernel<DT, true><<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale);
+    else
+      multi_tensor_copy_kernel<DT, false><<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, cudaStream_t s) {
+  if (nvec == 0) return cudaSuccess;
+  const int grid = clamp_grid((nvec + 2047) / 2048, 0, kNumSMs * 4);
+  local_copy_kernel<<<grid, 512, 0, s>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), nvec);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oneshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
+                           int dtype, int max_ctas, cudaStream_t s) {
+  const int grid = clamp_grid((nvec + kArThreads - 1) / kArThreads, max_ctas, 36);
+  B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
+                     oneshot_kernel<DT, WS><<<grid, kArThreads, 0, s>>>(pt, ctl, in_off, out_off, nvec);
+                   }));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_twoshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
+                           int dtype, int max_ctas, cudaStream_t s) {
+  const uint64_t slice = (nvec + ctl.world - 1) / ctl.world;
+  const uint64_t step = uint64_t(kArThreads) * kTwoShotUnroll;
+  const int grid = clamp_grid((slice + step - 1) / step, max_ctas, 72);
+  B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
+                     twoshot_kernel<DT, WS><<<grid, kArThreads, 0, s>>>(pt, ctl, in_off, out_off, nvec);
+                   }));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_twoshot_tma(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off,
+                               uint64_t nvec, int dtype, int max_ctas, cudaStream_t s) {
+  const uint64_t slice = (nvec + ctl.world - 1) / ctl.world;
+  const int grid = clamp_grid((slice + kTmaChunkVec - 1) / kTmaChunkVec, max_ctas, 36);
+  B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
+                     constexpr size_t smem = size_t(tma_stages(WS)) * WS * kTmaChunkBytes;
+                     twoshot_tma_kernel<DT, WS><<<grid, kTmaThreads, smem, s>>>(pt, ctl, in_off, out_off, nvec);
+                   }));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, uint64_t in_off, uint64_t out_off,
+                        uint64_t nvec, int dtype, int max_ctas, cudaStream_t s) {
+  const uint64_t slice = (nvec + ctl.world - 1) / ctl.world;
+  const uint64_t step = uint64_t(kArThreads) * kNvlsUnroll;
+  const int grid = clamp_grid((slice + step - 1) / step, max_ctas, 36);
+  B200_DISPATCH_DT(dtype, { nvls_kernel<DT><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec); });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fused(const TensorTable& tt, const PeerTable& pt, const Ctl& ctl, uint64_t bucket_off,
+                         uint32_t nvec, int dtype, float scale, cudaStream_t s) {
+  if (nvec == 0 || tt.n <= 0) return cudaSuccess;
+  const int grid = static_cast<int>((nvec + kFusedVecPerCta - 1) / kFusedVecPerCta);
+  if (grid > kMaxBlocks) return cudaErrorInvalidValue;
+  if (ctl.world == 1) {
+    B200_DISPATCH_DT(dtype, {
+      fused_bucket_kernel<DT, 1><<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale);
+    });
+  } else {
+    B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
+                       fused_bucket_kernel<DT, WS>
+                           <<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale);
+                     }));
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_broadcast(const PeerTable& pt, const Ctl& ctl, uint64_t off, uint64_t nvec, int root,
+                             int max_ctas, cudaStream_t s) {
+  const int grid = clamp_grid((nvec + kArThreads * 4 - 1) / (kArThreads * 4), max_ctas, 36);
+  broadcast_kernel<<<grid, kArThreads, 0, s>>>(pt, ctl, off, nvec, root);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_barrier(const PeerTable& pt, const Ctl& ctl, cudaStream_t s) {
+  barrier_kernel<<<1, 32, 0, s>>>(pt, ctl);
+  return cudaGetLastError();
+}
+
+namespace {
+template <int DT, int WS>
+cudaError_t opt_in_tma() {
+  constexpr int smem = tma_stages(WS) * WS * kTmaChunkBytes;
+  return cudaFuncSetAttribute(twoshot_tma_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+template <int DT>
+cudaError_t opt_in_tma_all_ws() {
+  cudaError_t e;
+  if ((e = opt_in_tma<DT, 2>()) != cudaSuccess) return e;
+  if ((e = opt_in_tma<DT, 3>()) != cudaSuccess) return e;
+  if ((e = opt_in_tma<DT, 4>()) != cudaSuccess) return e;
+  if ((e = opt_in_tma<DT, 5>()) != cudaSuccess) return e;
+  if ((e = opt_in_tma<DT, 6>()) != cudaSuccess) return e;
+  if ((e = opt_in_tma<DT, 7>()) != cudaSuccess) return e;
+  return opt_in_tma<DT, 8>();
+}
+}  // namespace
+
+cudaError_t prepare_kernels() {
+  cudaError_t e;
+  if ((e = opt_in_tma_all_ws<B200DDP_F32>()) != cudaSuccess) return e;
+  if ((e = opt_in_tma_all_ws<B200DDP_BF16>()) != cudaSuccess) return e;
+  return opt_in_tma_all_ws<B200DDP_F16>();
+}
+
+}  // namespace b200ddp

@@ -1,0 +1,172 @@
+"""``DistributedDataParallel`` — the drop-in for the one line the reference contributes to the hot path:
+``self.model = DDP(model, device_ids=[gpu_id])`` (ref:multigpu.py:36, ref:multigpu_torchrun.py:34,
+ref:multinode_torchrun.py:35, ref:multigpu_profile.py:39-42).
+
+It keeps the surface the reference scripts use — ``DDP(module, device_ids=[i])`` / ``DDP(module, [i])``,
+``ddp(inputs)``, ``.module``, ``state_dict()`` with ``module.``-prefixed keys (ref:multigpu_profile.py:77),
+gradients landing in the ORIGINAL ``Parameter.grad`` objects (the optimizer is built on the inner model
+before wrapping, ref:multigpu.py:68,84-86) — and the construction-time semantics of torch's class
+(torch:nn/parallel/distributed.py:661-960): parameter-shape verification, rank-0 parameter/buffer
+broadcast, per-forward buffer broadcast, ``no_sync()``.  Below that surface everything is ours: the
+custom ``Reducer`` and the sm_100a peer-to-peer kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import os
+from contextlib import contextmanager
+from typing import Any, Iterable, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .bucketing import DEFAULT_BUCKET_BYTES_CAP, DEFAULT_FIRST_BUCKET_BYTES
+from .reducer import BucketEngine, P2PEngine, Reducer, arena_bytes_for
+
+_live_ddp: List["DistributedDataParallel"] = []
+
+
+def _move(obj: Any, device: torch.device) -> Any:
+    if isinstance(obj, torch.Tensor):
+        return obj if obj.device == device else obj.to(device, non_blocking=True)
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_move(o, device) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _move(v, device) for k, v in obj.items()}
+    return obj
+
+
+class DistributedDataParallel(nn.Module):
+    def __init__(
+        self,
+        module: nn.Module,
+        device_ids: Optional[Sequence[Any]] = None,
+        output_device: Optional[Any] = None,
+        dim: int = 0,
+        broadcast_buffers: bool = True,
+        process_group: Any = None,
+        bucket_cap_mb: Optional[float] = None,
+        find_unused_parameters: bool = False,
+        check_reduction: bool = False,
+        gradient_as_bucket_view: bool = False,
+        static_graph: bool = False,
+        *,
+        _engine: Optional[BucketEngine] = None,
+    ) -> None:
+        super().__init__()
+        if find_unused_parameters:
+            raise NotImplementedError("find_unused_parameters=True is outside the reference's path "
+                                      "(DDP(model, device_ids=[gpu_id])) and is not supported")
+        if gradient_as_bucket_view:
+            raise NotImplementedError("gradient_as_bucket_view is not implemented yet (SURVEY §8 f.1)")
+        if process_group is not None:
+            raise NotImplementedError("b200ddp spans the default process group (one 8-GPU NVSwitch box)")
+        if device_ids is not None and len(device_ids) > 1:
+            raise ValueError("device_ids takes exactly one device (one process per GPU)")
+        self.module = module
+        self.dim = dim
+        self.broadcast_buffers = broadcast_buffers
+        self.static_graph = static_graph
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise RuntimeError("DistributedDataParallel is not needed when a module doesn't have any parameter "
+                               "that requires a gradient.")
+        devices = {p.device for p in params}
+        if len(devices) != 1:
+            raise ValueError(f"all parameters must live on one device, got {sorted(map(str, devices))}")
+        self.device = next(iter(devices))
+        if device_ids is not None:
+            want = torch.device(device_ids[0]) if not isinstance(device_ids[0], int) else torch.device("cuda", device_ids[0])
+            if _engine is None and want != self.device:
+                raise ValueError(f"device_ids={list(device_ids)} but the module's parameters are on {self.device}")
+        self.device_ids = list(device_ids) if device_ids is not None else None
+        self.output_device = output_device
+        cap = DEFAULT_BUCKET_BYTES_CAP if bucket_cap_mb is None else int(bucket_cap_mb * 1024 * 1024)
+        env_cap = os.environ.get("B200DDP_BUCKET_MB")
+        if env_cap and bucket_cap_mb is None:
+            cap = int(float(env_cap) * 1024 * 1024)
+        # an explicit cap also applies to the first bucket (torch:nn/parallel/distributed.py:1230-1236,1262-1266)
+        first = DEFAULT_FIRST_BUCKET_BYTES if bucket_cap_mb is None and not env_cap else cap
+        self.bucket_bytes_cap = cap
+
+        state = self._module_states()
+        if _engine is None:
+            # the arena also stages the construction-time / per-forward broadcasts
+            self.engine: BucketEngine = P2PEngine(self.device, arena_bytes_for(params))
+        else:
+            self.engine = _engine
+        self._verify_param_shapes(params)
+        # ranks start from different random initialisations (ref:multigpu.py:67); rank 0 wins
+        # (torch:nn/parallel/distributed.py:883-890)
+        self.engine.broadcast_tensors(state, root=0)
+        self.reducer = Reducer(params, self.engine, cap, first)
+        self.require_backward_grad_sync = True
+        _live_ddp.append(self)
+
+    # ---- construction helpers ------------------------------------------------------------------------
+    def _module_states(self) -> List[torch.Tensor]:
+        return [p.detach() for p in self.module.parameters()] + [b.detach() for b in self.module.buffers()]
+
+    def _verify_param_shapes(self, params: Iterable[torch.Tensor]) -> None:
+        """All ranks must wrap the same architecture (``_verify_param_shape_across_processes``,
+        torch:nn/parallel/distributed.py:881).  Host-side, through the c10d store."""
+        if self.engine.world_size == 1:
+            return
+        import hashlib
+
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            return
+        sig = hashlib.sha1(repr([(tuple(p.shape), str(p.dtype)) for p in params]).encode()).hexdigest()
+        sigs: List[Any] = [None] * dist.get_world_size()
+        store = dist.distributed_c10d._get_default_store()
+        uid = getattr(getattr(self.engine, "comm", None), "uid", None)
+        prefix = f"b200ddp/shapes/{uid}/{len(_live_ddp)}"
+        store.set(f"{prefix}/{dist.get_rank()}", sig)
+        for r in range(dist.get_world_size()):
+            sigs[r] = bytes(store.get(f"{prefix}/{r}")).decode()
+        if any(s != sigs[0] for s in sigs):
+            raise RuntimeError("DDP expects the same model across all ranks, but parameter shapes/dtypes differ "
+                               f"between ranks (signatures {sigs})")
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def forward(self, *inputs: Any, **kwargs: Any) -> Any:
+        if self.device_ids is not None:
+            inputs, kwargs = _move(inputs, self.device), _move(kwargs, self.device)
+        will_sync = torch.is_grad_enabled() and self.require_backward_grad_sync
+        if self.broadcast_buffers and will_sync:
+            buffers = [b for b in self.module.buffers()]
+            if buffers:
+                # torch:nn/parallel/distributed.py:1590-1591,2214-2256: rank 0's buffers before forward
+                self.engine.broadcast_tensors([b.detach() for b in buffers], root=0)
+        out = self.module(*inputs, **kwargs)
+        if torch.is_grad_enabled():
+            self.reducer.require_sync = self.require_backward_grad_sync
+            if self.require_backward_grad_sync:
+                self.reducer.prepare_for_backward()
+            else:
+                self.reducer.armed = False
+        return out
+
+    @contextmanager
+    def no_sync(self):
+        """Skip gradient synchronisation inside the context (gradients accumulate locally)."""
+        old = self.require_backward_grad_sync
+        self.require_backward_grad_sync = False
+        try:
+            yield
+        finally:
+            self.require_backward_grad_sync = old
+
+    # ---- teardown ------------------------------------------------------------------------------------
+    def shutdown(self) -> None:
+        """Release the arena (called by ``destroy_process_group``)."""
+        if self in _live_ddp:
+            _live_ddp.remove(self)
+        self.reducer.remove_hooks()
+        self.engine.close()
+
+
+def shutdown_all() -> None:
+    for ddp in list(_live_ddp):
+        ddp.shutdown()

@@ -1,0 +1,359 @@
+"""Custom gradient Reducer — the host side of the hot path.
+
+Mirrors the behaviour of ``c10d::Reducer`` as the reference's ``DDP(model)`` uses it
+(torch:include/torch/csrc/distributed/c10d/reducer.hpp): a post-accumulate hook per parameter
+(``autograd_hook``, :74) counts a bucket's pending gradients down (``mark_variable_ready``, :280); a
+bucket whose count reaches zero is launched as soon as all earlier buckets have been
+(``mark_bucket_ready``, :282, strict index order via ``next_bucket_``, :231); a callback queued on the
+autograd engine ends the iteration (``finalize_backward``, :286); after the first iteration the buckets
+are rebuilt once in the order gradients actually became ready (``rebuild_buckets``, :136,149-151) with
+rank 0's order made authoritative (``sync_bucket_indices``, :299-301).
+
+What differs is below the bucket: instead of one D2D copy per parameter into the bucket, an NCCL
+allreduce, and one copy per parameter back, a ready bucket is handed to a ``BucketEngine`` whose product
+implementation (``P2PEngine``) enqueues hand-written sm_100a kernels through the C ABI: one multi-tensor
+flatten(+1/ws scale), one peer-to-peer allreduce, one multi-tensor unflatten — or a single fused launch
+for small buckets.  There is no CPU or NCCL implementation of the engine in this package.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch.autograd import Variable
+
+from . import _lib
+from .bucketing import (
+    DEFAULT_BUCKET_BYTES_CAP,
+    DEFAULT_FIRST_BUCKET_BYTES,
+    BucketLayout,
+    BucketSpec,
+    compute_bucket_assignment_by_size,
+    layout_bucket,
+)
+from .comm import P2PComm, TensorTable, dtype_code
+
+
+class BucketEngine:
+    """What the Reducer needs from the layer that moves bytes.  ``P2PEngine`` is the only implementation
+    shipped; tests inject recording/gloo engines to exercise the host logic without a GPU."""
+
+    rank: int = 0
+    world_size: int = 1
+
+    def plan(self, buckets: List[BucketSpec]) -> None:
+        """Called whenever the bucket list changes (construction, rebuild)."""
+        raise NotImplementedError
+
+    def reduce_bucket(self, bucket: BucketSpec, grads: List[torch.Tensor]) -> None:
+        """Average ``grads`` (this bucket's gradients, in bucket order) over all ranks, in place.
+        Must only enqueue work ordered after the caller's current stream; must not block the host."""
+        raise NotImplementedError
+
+    def finalize(self) -> None:
+        """Make the caller's current stream wait for every bucket enqueued this iteration."""
+        raise NotImplementedError
+
+    def sync_order(self, order: List[int]) -> List[int]:
+        """Return rank 0's ``order`` on every rank (host-side, once)."""
+        raise NotImplementedError
+
+    def broadcast_tensors(self, tensors: Sequence[torch.Tensor], root: int = 0) -> None:
+        """Overwrite ``tensors`` on every rank with root's values."""
+        raise NotImplementedError
+
+    def close(self) -> None:
+        pass
+
+
+class P2PEngine(BucketEngine):
+    """The product engine: buckets live in the IPC-shared arena of a ``P2PComm`` and are reduced by the
+    sm_100a kernels of libb200ddp.so on a dedicated high-priority side stream."""
+
+    def __init__(self, device: torch.device, arena_bytes: int, comm: Optional[P2PComm] = None) -> None:
+        if device.type != "cuda":
+            raise RuntimeError("b200ddp reduces gradients on B200 GPUs only; module parameters must be on a "
+                               f"CUDA device (got {device}) — there is no CPU path")
+        self.device = device
+        self.comm = comm if comm is not None else P2PComm.from_process_group(arena_bytes, device.index)
+        self.rank, self.world_size = self.comm.rank, self.comm.world
+        self.scale = 1.0 / self.world_size
+        with torch.cuda.device(device):
+            self.stream = torch.cuda.Stream(device=device, priority=-1)
+        self._stream_ptr = self.stream.cuda_stream
+        self.max_ctas = int(os.environ.get("B200DDP_CTAS", "0"))
+        self._tables: Dict[int, TensorTable] = {}
+        self._order_seq = 0
+        self._fused_max = min(P2PComm.fused_max_bytes(), int(os.environ.get("B200DDP_FUSED_MAX", str(1 << 30))))
+        self._max_table = P2PComm.max_table_tensors()
+        self._keepalive: List[torch.Tensor] = []
+
+    # ---- planning -----------------------------------------------------------------------------------
+    def plan(self, buckets: List[BucketSpec]) -> None:
+        layout = BucketLayout()
+        for b in buckets:
+            b.fused = b.nbytes <= self._fused_max and len(b.param_indices) <= self._max_table
+            b.algo = _lib.ALGO_ONESHOT if b.fused else self.comm.pick_algo(b.nbytes)
+            if self.world_size == 1:
+                b.algo = _lib.ALGO_AUTO
+            layout.place(b, out_of_place=(not b.fused and b.algo == _lib.ALGO_ONESHOT and self.world_size > 1))
+        if layout.total_bytes > self.comm.arena_bytes:
+            raise RuntimeError(f"bucket layout needs {layout.total_bytes} bytes but the arena has "
+                               f"{self.comm.arena_bytes}")
+        self._tables.clear()
+
+    def _table(self, bucket: BucketSpec, tensors: Sequence[torch.Tensor]) -> TensorTable:
+        ptrs = [t.data_ptr() for t in tensors]
+        cached = self._tables.get(bucket.index)
+        if cached is not None and cached.key == tuple(ptrs):
+            return cached
+        table = TensorTable(ptrs, bucket.offsets_el, bucket.lengths_el)
+        self._tables[bucket.index] = table
+        return table
+
+    # ---- hot path -----------------------------------------------------------------------------------
+    def reduce_bucket(self, bucket: BucketSpec, grads: List[torch.Tensor]) -> None:
+        comm, s = self.comm, self._stream_ptr
+        work = grads
+        if not all(g.is_contiguous() for g in grads):
+            # rare layout (e.g. channels_last grads): reduce dense copies, copy back on the side stream
+            work = [g if g.is_contiguous() else g.contiguous() for g in grads]
+        comm.stream_wait(s, torch.cuda.current_stream(self.device).cuda_stream)
+        table = self._table(bucket, work)
+        if bucket.fused:
+            comm.fused_bucket(table, bucket.dtype_code, bucket.arena_off, bucket.nbytes, self.scale, s)
+        else:
+            comm.flatten_scale(table, bucket.dtype_code, bucket.arena_off, self.scale, s)
+            if self.world_size > 1:
+                comm.allreduce(bucket.arena_off, bucket.out_off, bucket.nbytes, bucket.dtype_code, bucket.algo,
+                               self.max_ctas, s)
+            comm.unflatten(table, bucket.dtype_code, bucket.out_off, s)
+        if work is not grads:
+            with torch.cuda.stream(self.stream):
+                for g, w in zip(grads, work):
+                    if w is not g:
+                        g.copy_(w)
+            self._keepalive.extend(work)
+
+    def finalize(self) -> None:
+        self.comm.stream_wait(torch.cuda.current_stream(self.device).cuda_stream, self._stream_ptr)
+        self._keepalive.clear()
+        self.comm.poll_error()
+
+    # ---- control plane (host side, rare) -------------------------------------------------------------
+    def sync_order(self, order: List[int]) -> List[int]:
+        if self.world_size == 1 or self.comm.uid is None:
+            return list(order)  # single rank, or an in-process loop-back world (tests)
+        import torch.distributed as dist
+
+        store = dist.distributed_c10d._get_default_store()
+        key = self._order_key()
+        if self.rank == 0:
+            store.set(key, ",".join(map(str, order)))
+            return list(order)
+        raw = bytes(store.get(key)).decode()
+        return [int(x) for x in raw.split(",")] if raw else []
+
+    def _order_key(self) -> str:
+        # identical on every rank: communicators are created collectively (comm.uid) and every rank
+        # asks for the order the same number of times
+        self._order_seq += 1
+        return f"b200ddp/order/c{self.comm.uid}/n{self._order_seq}"
+
+    def broadcast_tensors(self, tensors: Sequence[torch.Tensor], root: int = 0) -> None:
+        """Root's tensors -> every rank, staged through the arena in raw 4- or 2-byte elements (bit
+        exact for any dtype); tensors whose byte size is odd go through torch.distributed."""
+        if self.world_size == 1 or not tensors:
+            return
+        comm, s = self.comm, self._stream_ptr
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        comm.stream_wait(s, cur)
+        odd = [t for t in tensors if not t.is_contiguous() or (t.numel() * t.element_size()) % 2]
+        groups = {4: [], 2: []}
+        for t in tensors:
+            if any(t is o for o in odd):
+                continue
+            nbytes = t.numel() * t.element_size()
+            unit = 4 if nbytes % 4 == 0 and t.data_ptr() % 4 == 0 else 2
+            groups[unit].append(t)
+        cap = self.comm.arena_bytes
+        for unit, ts in groups.items():
+            code = _lib.F32 if unit == 4 else _lib.BF16
+            i = 0
+            while i < len(ts):
+                # greedily fill the arena, respecting the table limit
+                chunk, offs, lens, off = [], [], [], 0
+                while i < len(ts) and len(chunk) < self._max_table:
+                    n_el = ts[i].numel() * ts[i].element_size() // unit
+                    padded = (n_el * unit + 15) // 16 * 16
+                    if chunk and off * unit + padded > cap:
+                        break
+                    if padded > cap:
+                        raise RuntimeError("tensor larger than the broadcast arena")
+                    chunk.append(ts[i]); offs.append(off); lens.append(n_el)
+                    off += padded // unit
+                    i += 1
+                nbytes = max(off * unit, 16)
+                table = TensorTable([t.data_ptr() for t in chunk], offs, lens)
+                if self.rank == root:
+                    comm.flatten_scale(table, code, 0, 1.0, s)
+                comm.broadcast(0, nbytes, root, s, self.max_ctas)
+                if self.rank != root:
+                    comm.unflatten(table, code, 0, s)
+        comm.stream_wait(cur, s)
+        if odd:
+            import torch.distributed as dist
+
+            for t in odd:
+                dist.broadcast(t, src=root)
+
+    def close(self) -> None:
+        if self.comm is not None:
+            torch.cuda.synchronize(self.device)
+            self.comm.destroy()
+            self.comm = None
+
+
+class Reducer:
+    """Hooks, pending counts, in-order bucket launch, finalize, one-time rebuild."""
+
+    def __init__(
+        self,
+        params: Sequence[torch.nn.Parameter],
+        engine: BucketEngine,
+        bucket_bytes_cap: int = DEFAULT_BUCKET_BYTES_CAP,
+        first_bucket_bytes_cap: int = DEFAULT_FIRST_BUCKET_BYTES,
+    ) -> None:
+        self.params = list(params)
+        if not self.params:
+            raise RuntimeError("DistributedDataParallel is not needed when a module doesn't have any parameter "
+                               "that requires a gradient.")
+        self.engine = engine
+        self.bucket_bytes_cap = int(bucket_bytes_cap)
+        self.first_bucket_bytes_cap = int(first_bucket_bytes_cap)
+        self._sizes = [p.numel() * p.element_size() for p in self.params]
+        self._keys = [(p.dtype, p.device) for p in self.params]
+        # construction-time buckets: parameters in definition order, bucket list reversed so that bucket 0
+        # holds the last-defined parameters, whose gradients arrive first
+        # (torch:nn/parallel/distributed.py:1240-1257)
+        indices, _ = compute_bucket_assignment_by_size(
+            self._sizes, self._keys, [self.first_bucket_bytes_cap, self.bucket_bytes_cap])
+        self.buckets: List[BucketSpec] = []
+        self._install(list(reversed(indices)))
+        self.has_rebuilt = False
+        self.armed = False
+        self.require_sync = True
+        self._callback_queued = False
+        self._ready_order: List[int] = []
+        self._unfinished = False
+        self.iterations = 0
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+
+    # ---- bucket bookkeeping -------------------------------------------------------------------------
+    def _install(self, bucket_indices: List[List[int]]) -> None:
+        specs = []
+        for bi, idxs in enumerate(bucket_indices):
+            p0 = self.params[idxs[0]]
+            specs.append(layout_bucket(bi, idxs, [self.params[i].numel() for i in idxs], dtype_code(p0.dtype),
+                                       p0.element_size()))
+        self.engine.plan(specs)
+        self.buckets = specs
+        self._param_bucket = [0] * len(self.params)
+        for b in specs:
+            for i in b.param_indices:
+                self._param_bucket[i] = b.index
+        self._pending = [0] * len(specs)
+        self._bucket_ready = [False] * len(specs)
+        self._param_seen = [False] * len(self.params)
+        self._next_bucket = 0
+
+    def bucket_sizes(self) -> List[int]:
+        return [b.payload_bytes for b in self.buckets]
+
+    # ---- per-iteration protocol ----------------------------------------------------------------------
+    def prepare_for_backward(self) -> None:
+        """Arm the reducer for the backward of the forward that just ran
+        (Reducer::prepare_for_backward, called from DDP._post_forward, distributed.py:1648)."""
+        if self._unfinished:
+            raise RuntimeError(
+                "Expected to have finished reduction in the prior iteration before starting a new one. "
+                "Some parameters did not receive a gradient; b200ddp (like the reference's "
+                "DDP(model, device_ids=[gpu_id]), find_unused_parameters=False) requires every parameter "
+                "to take part in the loss.")
+        for b in self.buckets:
+            self._pending[b.index] = len(b.param_indices)
+            self._bucket_ready[b.index] = False
+        for i in range(len(self._param_seen)):
+            self._param_seen[i] = False
+        self._next_bucket = 0
+        self._callback_queued = False
+        self.armed = self.require_sync
+
+    def _make_hook(self, index: int):
+        def hook(param: torch.Tensor) -> None:
+            self._autograd_hook(index)
+        return hook
+
+    def _autograd_hook(self, index: int) -> None:
+        if not self.armed:
+            return
+        if not self._callback_queued:
+            self._callback_queued = True
+            self._unfinished = True
+            Variable._execution_engine.queue_callback(self._finalize_backward)
+        if self._param_seen[index]:
+            raise RuntimeError(f"parameter {index} was marked ready twice in one backward; b200ddp does not "
+                               "support re-entrant backward or shared use of a parameter across graphs")
+        self._param_seen[index] = True
+        if not self.has_rebuilt:
+            self._ready_order.append(index)
+        bi = self._param_bucket[index]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._bucket_ready[bi] = True
+            n = len(self.buckets)
+            while self._next_bucket < n and self._bucket_ready[self._next_bucket]:
+                b = self.buckets[self._next_bucket]
+                self.engine.reduce_bucket(b, [self.params[i].grad for i in b.param_indices])
+                self._next_bucket += 1
+
+    def _finalize_backward(self) -> None:
+        if not self.armed:
+            return
+        self.armed = False
+        if self._next_bucket != len(self.buckets):
+            missing = [i for i, seen in enumerate(self._param_seen) if not seen]
+            # leave _unfinished set: the next forward raises, like DDP does
+            self.engine.finalize()
+            raise RuntimeError(f"backward finished but {len(missing)} parameter(s) never produced a gradient "
+                               f"(indices {missing[:8]}...); find_unused_parameters is not supported")
+        self.engine.finalize()
+        self._unfinished = False
+        self.iterations += 1
+        if not self.has_rebuilt:
+            self._rebuild_buckets()
+
+    def _rebuild_buckets(self) -> None:
+        """One-time re-bucketing in gradient-ready order (rank 0's order wins on every rank)."""
+        order = self.engine.sync_order(self._ready_order)
+        self._ready_order = []
+        self.has_rebuilt = True
+        if sorted(order) != list(range(len(self.params))):
+            return  # incomplete order (should not happen once finalize succeeded): keep current buckets
+        sizes = [self._sizes[i] for i in order]
+        keys = [self._keys[i] for i in order]
+        indices, _ = compute_bucket_assignment_by_size(
+            sizes, keys, [self.first_bucket_bytes_cap, self.bucket_bytes_cap], tensor_indices=order)
+        self._install(indices)
+
+    def remove_hooks(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def arena_bytes_for(params: Sequence[torch.nn.Parameter]) -> int:
+    """Arena size that fits any bucketing of ``params`` (in + out region per bucket, region alignment)."""
+    payload = sum((p.numel() * p.element_size() + 15) // 16 * 16 for p in params)
+    return 2 * (payload + len(params) * BucketLayout.REGION_ALIGN) + (1 << 20)
