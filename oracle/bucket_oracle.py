@@ -13,7 +13,10 @@ Rules restated:
   R4  after appending a tensor, if the accumulated byte size >= the key's current limit the bucket is
       emitted with that limit, the accumulator restarts empty, and the key advances to the next limit
       unless it already is at the last one;
-  R5  at the end every non-empty accumulator is emitted with the limit it was last compared against;
+  R5  at the end every non-empty accumulator is emitted with the limit it was last compared against
+      (torch walks a std::unordered_map here, so with SEVERAL keys and ready-order input the order of these
+      trailing buckets is implementation defined; this restatement emits them in first-seen key order —
+      membership and limits are pinned by the golden vectors, see tests/test_oracle_golden.py);
   R6  if tensor_indices was NOT given, emitted buckets are ordered by their smallest tensor index;
       otherwise emission order is kept (gradient-ready order).
 """

@@ -57,6 +57,11 @@ def _worker(rank: int, world: int, port: int, spec: Dict, ret) -> None:
         rec: Dict[str, List] = {"ddp_grads": [], "local_grads": [], "weights": [], "loss": []}
         steps, warmup = spec["steps"], spec.get("warmup", 0)
         fixed = make_batch(bsz, device, gen) if spec.get("fixed_batch") else None
+        # timing runs draw from a pre-generated pool so that batch synthesis stays outside the step,
+        # as in the product arm (recording runs keep one fresh batch per step)
+        pool = None
+        if not spec.get("record") and fixed is None:
+            pool = [make_batch(bsz, device, gen) for _ in range(min(warmup + steps, 64))]
         t0 = None
         for step in range(warmup + steps):
             if step == warmup:
@@ -64,7 +69,10 @@ def _worker(rank: int, world: int, port: int, spec: Dict, ret) -> None:
                     torch.cuda.synchronize()
                 dist.barrier()
                 t0 = time.perf_counter()
-            x, y = fixed if fixed is not None else make_batch(bsz, device, gen)
+            if pool is not None:
+                x, y = pool[step % len(pool)]
+            else:
+                x, y = fixed if fixed is not None else make_batch(bsz, device, gen)
             if shadow is not None:
                 shadow.load_state_dict(model.state_dict())
                 shadow.zero_grad()

@@ -77,7 +77,7 @@ def bucket_cases():
         c["expect_buckets"] = [list(b) for b in buckets]
         c["expect_limits"] = list(limits)
     with open(os.path.join(HERE, "bucket_assignment.json"), "w") as f:
-        json.dump(dict(torch=torch.__version__, cases=cases), f)
+        json.dump(dict(torch=str(torch.__version__), cases=cases), f)
     print("bucket_assignment.json:", len(cases), "cases")
 
 
@@ -131,7 +131,7 @@ def ref_trainer():
             ret = mgr.dict()
             mp.spawn(_ref_trainer_worker, args=(2, free_port(), loss_name, steps, ret), nprocs=2, join=True)
             out[loss_name] = {r: dict(ret[r]) for r in range(2)}
-    torch.save(dict(torch=torch.__version__, world=2, seed_rule="torch.manual_seed(1234 + rank) before load_train_objs",
+    torch.save(dict(torch=str(torch.__version__), world=2, seed_rule="torch.manual_seed(1234 + rank) before load_train_objs",
                     cases=out), os.path.join(HERE, "ref_trainer_ws2.pt"))
     g = out["mse"][0]["ddp_grads"][0]
     print("ref_trainer_ws2.pt: mse grad absmax", max(float(t.abs().max()) for t in g),
@@ -148,7 +148,7 @@ def stock_mlp():
     assert same, "stock DDP produced different gradients on different ranks"
     keep = {r: dict(local_grads=out[r]["record"]["local_grads"]) for r in out}
     keep[0]["ddp_grads"] = out[0]["record"]["ddp_grads"]
-    torch.save(dict(torch=torch.__version__, world=3, workload="mlp", seed=77, batch_size=16, ranks=keep),
+    torch.save(dict(torch=str(torch.__version__), world=3, workload="mlp", seed=77, batch_size=16, ranks=keep),
                os.path.join(HERE, "stock_ddp_mlp_ws3.pt"))
     print("stock_ddp_mlp_ws3.pt written")
 

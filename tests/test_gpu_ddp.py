@@ -1,0 +1,192 @@
+"""GPU tests of the whole path through the reference-facing surface: the ``Trainer`` / ``DDP`` drop-in on
+one B200 (world 1), a 2-rank loop-back world replaying the golden vectors recorded from the reference's
+own Trainer, and — when the box has more than one GPU — real one-process-per-GPU worlds compared with
+stock torch-DDP over NCCL on the same seeds (the parity target north_star names)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def pg1():
+    """A world-size-1 process group through OUR ddp_setup (ref:multigpu.py:12-20)."""
+    from b200ddp import destroy_process_group, multigpu
+    from oracle.ref_ddp import free_port
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(free_port())
+    multigpu.ddp_setup(0, 1)
+    yield
+    destroy_process_group()
+
+
+def test_trainer_world1_matches_plain_training_bitwise(pg1):
+    from b200ddp import multigpu, utils
+
+    torch.manual_seed(0)
+    ds = utils.MyTrainDataset(256, seed=3)
+    model = torch.nn.Linear(20, 1)
+    plain = copy.deepcopy(model).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    popt = torch.optim.SGD(plain.parameters(), lr=1e-3)
+    loader = multigpu.prepare_dataloader(ds, 32)
+    multigpu.Trainer.loss_fn = staticmethod(torch.nn.MSELoss())  # CE gives all-zero grads
+    try:
+        trainer = multigpu.Trainer(model, loader, opt, 0, save_every=10**9)
+        comm = trainer.model.engine.comm
+        n0 = comm.launch_count
+        steps = 0
+        for x, y in loader:
+            x, y = x.cuda(), y.cuda()
+            trainer._run_batch(x, y)
+            popt.zero_grad()
+            torch.nn.functional.mse_loss(plain(x), y).backward()
+            popt.step()
+            steps += 1
+        torch.cuda.synchronize()
+        assert steps == 8
+        assert comm.launch_count - n0 == steps  # one fused launch per step for the 84-byte bucket
+        for p, q in zip(trainer.model.module.parameters(), plain.parameters()):
+            assert torch.equal(p, q)
+        assert float(next(plain.parameters()).grad.abs().max()) > 0
+        assert list(trainer.model.state_dict()) == ["module.weight", "module.bias"]
+        trainer.train(1)  # the surface's epoch loop runs
+    finally:
+        multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
+
+
+def test_world1_multibucket_three_kernel_path_bitwise(pg1):
+    from b200ddp import DDP, workloads
+
+    wl = workloads.get("mlp")
+    torch.manual_seed(1)
+    model = torch.nn.Sequential(torch.nn.Linear(20, 512), torch.nn.ReLU(), torch.nn.Linear(512, 512), torch.nn.ReLU(),
+                                torch.nn.Linear(512, 7)).cuda()
+    plain = copy.deepcopy(model)
+    ddp = DDP(model, device_ids=[0], bucket_cap_mb=0.5)
+    gen = torch.Generator().manual_seed(5)
+    for step in range(3):
+        x, y = wl.batch(16, torch.device("cuda"), gen)
+        ddp.zero_grad()
+        plain.zero_grad()
+        wl.loss(ddp(x), y).backward()
+        wl.loss(plain(x), y).backward()
+        torch.cuda.synchronize()
+        for p, q in zip(model.parameters(), plain.parameters()):
+            assert torch.equal(p.grad, q.grad)
+    sizes = ddp.reducer.bucket_sizes()
+    assert len(sizes) >= 2 and any(not b.fused for b in ddp.reducer.buckets)
+    assert ddp.reducer.has_rebuilt
+    ddp.shutdown()
+
+
+def test_product_path_requires_cuda_module(pg1):
+    from b200ddp import DDP
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DDP(torch.nn.Linear(4, 2))
+
+
+def test_loopback_ws2_replays_reference_trainer():
+    """Two ranks on one GPU, each with its own stream, model replica, Reducer and arena context; inputs,
+    initial weights and expected gradients are the golden vectors of the REFERENCE's Trainer (ws=2)."""
+    from b200ddp import DDP
+    from b200ddp.comm import P2PComm
+    from b200ddp.reducer import P2PEngine
+    from oracle import allreduce_oracle as ao
+    from tests.helpers import rel_err
+
+    fx = torch.load(os.path.join(GOLD, "ref_trainer_ws2.pt"))["cases"]["mse"]
+    dev = torch.device("cuda", 0)
+    comms = P2PComm.loopback_world(2, 0, 8 << 20)
+    for c in comms:
+        c.set_timeout_ms(10000)
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    models, ddps, opts = [], [], []
+    for r in range(2):
+        torch.manual_seed(50 + r)
+        m = torch.nn.Linear(20, 1)
+        if r == 0:
+            m.load_state_dict({"weight": fx[0]["w_before"][0][0], "bias": fx[0]["w_before"][0][1]})
+        m = m.cuda()
+        models.append(m)
+        opts.append(torch.optim.SGD(m.parameters(), lr=1e-3))
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            ddps.append(DDP(models[r], device_ids=[0], _engine=P2PEngine(dev, 0, comm=comms[r])))
+    torch.cuda.synchronize()
+    for p, q in zip(models[0].parameters(), models[1].parameters()):
+        assert torch.equal(p, q), "construction-time rank-0 broadcast over the P2P arena failed"
+    for step in range(4):
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                x, y = fx[r]["x"][step].cuda(), fx[r]["y"][step].cuda()
+                opts[r].zero_grad()
+                torch.nn.functional.mse_loss(ddps[r](x), y).backward()
+        torch.cuda.synchronize()
+        per_rank = [[g.numpy() for g in fx[r]["local_grads"][step]] for r in range(2)]
+        oracle = ao.ddp_average(per_rank)
+        for r in range(2):
+            for p, ref, orc in zip(models[r].parameters(), fx[r]["ddp_grads"][step], oracle):
+                assert rel_err(p.grad.cpu(), ref) <= 1e-6  # vs the reference stack (north_star tolerance)
+                # vs the oracle: local gradients come from cuBLAS here and from CPU BLAS in the fixture, so
+                # the inputs differ in the last bits; the kernel arithmetic itself is pinned bit-exactly in
+                # test_gpu_kernels.py
+                assert rel_err(p.grad.cpu(), torch.from_numpy(orc).view_as(ref)) <= 1e-6
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                opts[r].step()
+    torch.cuda.synchronize()
+    for p, q in zip(models[0].parameters(), models[1].parameters()):
+        assert torch.equal(p, q)
+    for r in range(2):
+        for p, ref in zip(models[r].parameters(), fx[r]["w_after"][3]):
+            assert torch.allclose(p.cpu(), ref, rtol=0, atol=1e-6)
+    for d in ddps:
+        d.shutdown()
+
+
+# ---------------------------------------------------------------------------------------------------
+# real multi-GPU worlds (skipped on a 1-GPU box; run with gpurun --gpus N)
+# ---------------------------------------------------------------------------------------------------
+def _spawn_mp(fn_name, world, **kw):
+    from oracle.ref_ddp import free_port
+    from tests import gpu_mp_worker
+
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(gpu_mp_worker.entry, args=(world, free_port(), fn_name, kw, ret), nprocs=world, join=True)
+        return {r: ret[r] for r in range(world)}
+
+
+needs_multi = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+
+
+@needs_multi
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("mem", ["vmm", "ipc"])
+def test_multigpu_raw_allreduce_all_algorithms(mem):
+    world = min(torch.cuda.device_count(), 8)
+    out = _spawn_mp("raw_allreduce", world, mem=mem)
+    for r in range(world):
+        assert out[r]["ok"], out[r]
+    assert out[0]["mem_mode"] == mem
+
+
+@needs_multi
+@pytest.mark.timeout(900)
+def test_multigpu_ddp_matches_stock_nccl_ddp():
+    world = min(torch.cuda.device_count(), 8)
+    out = _spawn_mp("ddp_vs_nccl", world)
+    for r in range(world):
+        assert out[r]["worst_rel"] <= 1e-6, out[r]
+        assert out[r]["weights_equal_across_ranks"]

@@ -1,0 +1,178 @@
+"""Host logic of the custom Reducer and the DDP wrapper, exercised on CPU with test engines
+(tests/helpers.py): hook/pending/ordering protocol, one-time rebuild, error paths, surface."""
+import inspect
+
+import pytest
+import torch
+import torch.nn as nn
+
+from b200ddp import DDP
+from b200ddp.bucketing import BucketLayout, layout_bucket
+from tests.helpers import RecordingEngine
+
+
+def _mlp():
+    torch.manual_seed(0)
+    return nn.Sequential(nn.Linear(20, 96), nn.ReLU(), nn.Linear(96, 96), nn.ReLU(), nn.Linear(96, 7))
+
+
+def _step(ddp, x=None):
+    x = torch.randn(8, 20) if x is None else x
+    ddp.zero_grad()
+    ddp(x).square().mean().backward()
+
+
+def test_initial_buckets_follow_reverse_definition_order_and_rebuild_once():
+    eng = RecordingEngine()
+    ddp = DDP(_mlp(), bucket_cap_mb=0.01, _engine=eng)  # ~10 KB cap -> several buckets
+    sizes0 = [b.param_indices for b in eng.plans[0]]
+    # construction: greedy over definition order, list reversed (bucket 0 = last parameters)
+    flat = [i for b in sizes0 for i in b]
+    assert sorted(flat) == list(range(6))
+    assert sizes0[0][-1] == 5 and sizes0[-1][0] == 0
+    _step(ddp)
+    # launches happened strictly in bucket-index order and covered every bucket
+    assert eng.launched == list(range(len(sizes0)))
+    assert eng.finalized == 1
+    # one rebuild after iteration 0, in gradient-ready order (reverse of definition for a chain)
+    assert len(eng.plans) == 2 and ddp.reducer.has_rebuilt
+    ready = [i for b in eng.plans[1] for i in b.param_indices]
+    assert ready == [5, 4, 3, 2, 1, 0]
+    eng.launched.clear()
+    _step(ddp)
+    assert eng.launched == list(range(len(eng.plans[1])))
+    assert len(eng.plans) == 2  # never rebuilt again
+
+
+def test_default_caps_give_one_bucket_for_toy_model():
+    eng = RecordingEngine()
+    ddp = DDP(nn.Linear(20, 1), _engine=eng)
+    assert [b.param_indices for b in eng.plans[0]] == [[0, 1]]
+    assert ddp.reducer.bucket_sizes() == [84]  # toy = 1 bucket x 84 B
+
+
+def test_grads_land_in_original_parameters_and_surface():
+    model = _mlp()
+    opt_params = list(model.parameters())
+    ddp = DDP(model, device_ids=None, _engine=RecordingEngine())
+    assert ddp.module is model
+    assert all(a is b for a, b in zip(opt_params, ddp.module.parameters()))
+    assert all(k.startswith("module.") for k in ddp.state_dict())  # ref:multigpu_profile.py:77
+    assert list(ddp.module.state_dict()) == [k[len("module."):] for k in ddp.state_dict()]
+    _step(ddp)
+    assert all(p.grad is not None for p in opt_params)
+    ref = _mlp()
+    x = torch.randn(8, 20)
+    _step(ddp, x)
+    ref(x).square().mean().backward()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert torch.equal(p.grad, q.grad)  # ws=1 recording engine leaves grads untouched
+
+
+def test_out_of_order_ready_still_launches_in_index_order():
+    eng = RecordingEngine()
+    model = _mlp()
+    ddp = DDP(model, bucket_cap_mb=0.01, _engine=eng)
+    _step(ddp)  # rebuild happens here
+    eng.launched.clear()
+    # fire hooks by hand in an order where a later bucket completes first
+    ddp(torch.randn(2, 20))
+    red = ddp.reducer
+    for p in model.parameters():
+        p.grad = torch.zeros_like(p)
+    last = red.buckets[-1]
+    for i in last.param_indices:
+        red._param_seen[i] = True
+        red._pending[last.index] -= 1
+    red._bucket_ready[last.index] = red._pending[last.index] == 0
+    assert eng.launched == []  # bucket 0 not ready yet -> nothing may launch (strict order, reducer.hpp:231)
+
+
+def test_unused_parameter_raises_like_ddp():
+    class Partial(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(4, 4), nn.Linear(4, 4)
+
+        def forward(self, x):
+            return self.a(x)
+
+    ddp = DDP(Partial(), _engine=RecordingEngine())
+    with pytest.raises(RuntimeError, match="never produced a gradient"):
+        ddp(torch.randn(2, 4)).sum().backward()
+    with pytest.raises(RuntimeError, match="finished reduction in the prior iteration"):
+        ddp(torch.randn(2, 4))
+
+
+def test_no_sync_skips_reduction_and_accumulates():
+    eng = RecordingEngine()
+    ddp = DDP(_mlp(), _engine=eng)
+    x = torch.randn(4, 20)
+    with ddp.no_sync():
+        ddp(x).sum().backward()
+    assert eng.launched == [] and eng.finalized == 0
+    ddp(x).sum().backward()
+    assert eng.launched and eng.finalized == 1
+
+
+def test_backward_without_forward_does_not_reduce():
+    eng = RecordingEngine()
+    model = _mlp()
+    ddp = DDP(model, _engine=eng)
+    model(torch.randn(2, 20)).sum().backward()  # inner module called directly: reducer not armed
+    assert eng.launched == []
+
+
+def test_constructor_argument_errors():
+    with pytest.raises(NotImplementedError):
+        DDP(_mlp(), find_unused_parameters=True, _engine=RecordingEngine())
+    with pytest.raises(ValueError):
+        DDP(_mlp(), device_ids=[0, 1], _engine=RecordingEngine())
+    frozen = nn.Linear(2, 2)
+    for p in frozen.parameters():
+        p.requires_grad_(False)
+    with pytest.raises(RuntimeError, match="doesn't have any parameter"):
+        DDP(frozen, _engine=RecordingEngine())
+
+
+def test_bucket_layout_alignment():
+    spec = layout_bucket(0, [0, 1, 2], [20, 1, 5], dtype_code=0, elem_size=4)
+    assert spec.offsets_el == [0, 20, 24] and spec.nbytes == 32 * 4
+    spec16 = layout_bucket(0, [0, 1], [3, 9], dtype_code=1, elem_size=2)
+    assert spec16.offsets_el == [0, 8] and spec16.nbytes == 48
+    lay = BucketLayout()
+    lay.place(spec, out_of_place=True)
+    assert spec.arena_off == 0 and spec.out_off == 4096 and lay.total_bytes == 8192
+    lay.place(spec16, out_of_place=False)
+    assert spec16.arena_off == spec16.out_off == 8192
+
+
+def test_script_surface_matches_reference_signatures():
+    """Names and signatures of the reference scripts (ref:multigpu.py, ref:multigpu_torchrun.py, ref:utils.py)."""
+    from b200ddp import multigpu, multigpu_torchrun, utils
+
+    def params(fn):
+        return list(inspect.signature(fn).parameters)
+
+    assert params(multigpu.ddp_setup) == ["rank", "world_size"]
+    assert params(multigpu.Trainer.__init__) == ["self", "model", "train_data", "optimizer", "gpu_id", "save_every"]
+    assert params(multigpu.main) == ["rank", "world_size", "save_every", "total_epochs"]
+    assert params(multigpu.prepare_dataloader) == ["dataset", "batch_size"]
+    assert params(multigpu.load_train_objs) == []
+    assert params(multigpu_torchrun.ddp_setup) == []
+    assert params(multigpu_torchrun.Trainer.__init__) == ["self", "model", "train_data", "optimizer", "save_every",
+                                                          "snapshot_path"]
+    assert params(multigpu_torchrun.main) == ["save_every", "total_epochs", "snapshot_path"]
+    for cls in (multigpu.Trainer, multigpu_torchrun.Trainer):
+        for m in ("_run_batch", "_run_epoch", "train"):
+            assert callable(getattr(cls, m))
+    assert hasattr(multigpu.Trainer, "_save_checkpoint") and hasattr(multigpu_torchrun.Trainer, "_save_snapshot")
+    ds, model, opt = multigpu.load_train_objs()
+    assert len(ds) == 2048 and isinstance(model, nn.Linear) and isinstance(opt, torch.optim.SGD)
+    x, y = ds[0]
+    assert x.shape == (20,) and y.shape == (1,) and 0 <= float(x.min()) and float(x.max()) < 1
+    rd = utils.MyRandomDataset(4, (3, 8, 8))
+    a, b = rd[0]
+    assert a.shape == (3, 8, 8) and b.shape == (1000,)
+    loader = multigpu.prepare_dataloader(utils.MyTrainDataset(64, seed=1), 32) if torch.distributed.is_initialized() else None
+    assert loader is None or loader.batch_size == 32
