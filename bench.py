@@ -33,6 +33,15 @@ import subprocess
 import sys
 import time
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -68,7 +77,7 @@ def default_steps(workload: str):
 # clocks
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -80,11 +89,15 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
         return self
+
+    def mark(self):
+        """Wall-clock bounds of the timed region; samples outside are dropped."""
+        self.marks = getattr(self, "marks", []) + [time.time()]
 
     def stop(self):
         if self.proc is None:
@@ -97,10 +110,22 @@ class ClockSampler:
             out, _ = self.proc.communicate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
+
+        marks = getattr(self, "marks", [])
+        total = 0
         for line in out.splitlines():
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
+            total += 1
+            if len(marks) >= 2:
+                try:
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    ts = None
+                if ts is not None and not (marks[0] - 0.15 <= ts <= marks[-1] + 0.15):
+                    continue
             try:
                 sm.append(float(parts[1]))
                 mx.append(float(parts[2]))
@@ -164,7 +189,7 @@ def main_reference(args):
                                    f"{r['threads_per_rank']} threads, Trainer loop restated in oracle/ref_ddp.py"},
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -180,7 +205,7 @@ def main_b200(args):
     from b200ddp.comm import P2PComm, TensorTable
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the b200ddp path has no CPU fallback"}))
+        emit({"error": "no CUDA device: the b200ddp path has no CPU fallback"})
         return 2
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
@@ -248,10 +273,12 @@ def main_b200(args):
         return float(t.item())
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------------
+    clocks = ClockSampler(local).start() if rank == 0 else None
     for i in range(warmup):
         trainer._run_batch(*dev_batches[i % len(dev_batches)])
     barrier_sync()
-    clocks = ClockSampler(local).start() if rank == 0 else None
+    if clocks:
+        clocks.mark()
     n0 = comm.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -259,6 +286,8 @@ def main_b200(args):
         trainer._run_batch(*dev_batches[i % len(dev_batches)])
     e1.record()
     barrier_sync()
+    if clocks:
+        clocks.mark()
     launches = comm.launch_count - n0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clock_info = clocks.stop() if clocks else None
@@ -363,7 +392,7 @@ def main_b200(args):
         best = max(big, key=lambda s: s["bytes"])
         line["roofline_large_bucket"] = {k: best[k] for k in ("kernel", "bytes", "bound", "achieved", "peak", "frac", "unit")}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     multigpu_torchrun.destroy_process_group()
     return 0
 
@@ -463,6 +492,12 @@ def bucket_sweep(torch, dist, comm_factory, world, rank, dev, hbm_peak, max_mib,
 
 def main():
     args = parse_args()
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner) and child
+    # processes write to fd 1 too, so fd 1 is pointed at stderr and the line goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return main_reference(args)
     return main_b200(args)

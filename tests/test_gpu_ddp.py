@@ -184,9 +184,12 @@ def test_multigpu_raw_allreduce_all_algorithms(mem):
 
 @needs_multi
 @pytest.mark.timeout(900)
-def test_multigpu_ddp_matches_stock_nccl_ddp():
+@pytest.mark.parametrize("workload", ["mlp", "slices"])
+def test_multigpu_ddp_matches_stock_nccl_ddp(workload):
+    """mlp: fused small buckets; slices: 64 MiB of gradients in 1 MiB + 25 MiB buckets (one-shot and the
+    large-bucket algorithm AUTO picks, NVLS when the fabric has it)."""
     world = min(torch.cuda.device_count(), 8)
-    out = _spawn_mp("ddp_vs_nccl", world)
+    out = _spawn_mp("ddp_vs_nccl", world, workload=workload)
     for r in range(world):
         assert out[r]["worst_rel"] <= 1e-6, out[r]
         assert out[r]["weights_equal_across_ranks"]
