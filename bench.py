@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("B200DDP_BENCH_WORKLOAD", "toy"), choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (auto: on for the launch-bound toy workload)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the bucket-size sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-max-mib", type=int, default=256)
@@ -273,23 +275,40 @@ def main_b200(args):
         return float(t.item())
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------------
+    use_graph = args.graph == "on" or (args.graph == "auto" and args.workload == "toy")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_steps(n):
+        """EXACTLY n steps bracketed by barrier + synchronize; device time, max over ranks."""
+        barrier_sync()
+        e0.record()
+        for i in range(n):
+            trainer._run_batch(*dev_batches[i % len(dev_batches)])
+        e1.record()
+        barrier_sync()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     clocks = ClockSampler(local).start() if rank == 0 else None
     for i in range(warmup):
         trainer._run_batch(*dev_batches[i % len(dev_batches)])
+    eager = None
+    if use_graph:
+        # eager number first (for the record), then capture: zero_grad/forward/loss/backward with the bucket
+        # kernels/SGD step become ONE graph launch; every replay does the same work on a new batch
+        eager_ms = timed_steps(steps)
+        eager = {"value": bsz * world * steps / (eager_ms / 1e3), "ms_per_step": eager_ms / steps,
+                 "note": "same step launched eagerly (no CUDA graph)"}
+        trainer.enable_cuda_graph(*dev_batches[0])
+        for i in range(warmup):
+            trainer._run_batch(*dev_batches[i % len(dev_batches)])
     barrier_sync()
     if clocks:
         clocks.mark()
     n0 = comm.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        trainer._run_batch(*dev_batches[i % len(dev_batches)])
-    e1.record()
-    barrier_sync()
+    ms_total = timed_steps(steps)
     if clocks:
         clocks.mark()
-    launches = comm.launch_count - n0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = (trainer.graph_kernel_launches * steps) if use_graph else (comm.launch_count - n0)
     clock_info = clocks.stop() if clocks else None
     value = bsz * world * steps / (ms_total / 1e3)
 
@@ -312,6 +331,7 @@ def main_b200(args):
 
     # ---- roofline of the step's dominant kernel: per-launch events on the launching stream -------------
     roof_steps = min(steps, 200)
+    trainer._graph = None  # the per-launch events need eager launches of the same kernels
     engine = ddp.engine
     pairs = []
     orig_reduce = engine.reduce_bucket
@@ -381,11 +401,11 @@ def main_b200(args):
         "config": {"workload": WORKLOAD_DESC[args.workload], "global_batch": bsz * world,
                    "parallelism": f"dp{world}", "bucket_bytes": ddp.reducer.bucket_sizes(),
                    "bucket_algos": [("fused" if b.fused else b.algo) for b in ddp.reducer.buckets],
-                   "mem_mode": comm.mem_mode, "multicast": comm.has_multicast,
+                   "mem_mode": comm.mem_mode, "multicast": comm.has_multicast, "cuda_graph": use_graph,
                    "l2": "training steps are not L2-flushed (each step consumes a different batch; weights are "
                          "the step's own state); bucket_sweep rotates buffers totalling > 126 MB L2"},
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-        "bucket_sweep": sweep, "cpu_baseline": cpu,
+        "bucket_sweep": sweep, "cpu_baseline": cpu, "eager": eager,
     }
     big = [s for s in sweep if s.get("frac") is not None]
     if big:
@@ -398,10 +418,16 @@ def main_b200(args):
 
 
 def bucket_sweep(torch, dist, comm_factory, world, rank, dev, hbm_peak, max_mib, lib, TensorTable):
-    """Kernel time vs bucket size with per-launch CUDA events on the launching stream.
+    """Kernel time vs bucket size.  `iters` launches (rotating through > L2 of distinct buffers) are captured
+    into ONE CUDA graph and the replay is timed with CUDA events on the replaying stream: per-launch time =
+    replay time / iters.  This keeps the host (ctypes launch + event records, and the skew between the
+    ranks' Python loops) out of a microsecond-scale measurement; the launches are graph-capturable because
+    the kernels keep their barrier generation in device memory.
     N=1: flatten and unflatten (HBM roofline, algorithmic bytes 2 S each).  N>1: each allreduce algorithm
-    (bus GB/s = S * 2 (ws-1)/ws / t against 900 GB/s per direction).  Buffers rotate through > L2."""
+    (bus GB/s = S * 2 (ws-1)/ws / t against 900 GB/s per direction) and NCCL on the same box."""
     sizes = [m << 20 for m in (1, 4, 16, 64, 256) if m <= max_mib]
+    if world > 1:
+        sizes = [256 << 10] + sizes
     biggest = max(sizes)
     slots = max(2, (288 << 20) // biggest + 1)  # rotate through >= 288 MiB of distinct arena
     arena = biggest * slots + (8 << 20) if world > 1 else 2 * biggest + (8 << 20)
@@ -410,17 +436,35 @@ def bucket_sweep(torch, dist, comm_factory, world, rank, dev, hbm_peak, max_mib,
     sp = stream.cuda_stream
     out = []
 
-    def time_launches(fn, iters):
-        evs = []
-        for i in range(iters):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            fn(i)
-            b.record(stream)
-            evs.append((a, b))
-        stream.synchronize()
-        ts = [a.elapsed_time(b) for a, b in evs]
-        return statistics.median(ts)
+    def time_graph(fn, iters, replays=5):
+        """median over `replays` of (graph replay time / iters), max over ranks, in ms"""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for i in range(iters):
+                fn(i)
+        ts = []
+        with torch.cuda.stream(stream):
+            for rep in range(replays + 2):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                g.replay()
+                b.record(stream)
+                stream.synchronize()
+                if rep >= 2:
+                    ts.append(a.elapsed_time(b) / iters)
+        ms = statistics.median(ts)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        del g
+        return ms
+
+    def iters_for(S):
+        return 40 if S <= (4 << 20) else (20 if S <= (64 << 20) else 8)
 
     if world == 1:
         for S in sizes:
@@ -430,18 +474,16 @@ def bucket_sweep(torch, dist, comm_factory, world, rank, dev, hbm_peak, max_mib,
             srcs = [[torch.rand(per, device=dev) for _ in range(n_t)] for _ in range(reps)]
             offs = [i * per for i in range(n_t)]
             tables = [TensorTable([t.data_ptr() for t in ts], offs, [per] * n_t) for ts in srcs]
-            iters = 20 if S <= (64 << 20) else 10
             for name, fn in (("flatten_scale", lambda i: comm.flatten_scale(tables[i % reps], lib.F32, 0, 0.5, sp)),
                              ("unflatten", lambda i: comm.unflatten(tables[i % reps], lib.F32, 0, sp))):
-                time_launches(fn, 3)
-                ms = time_launches(fn, iters)
+                ms = time_graph(fn, max(iters_for(S), reps))  # one replay streams > L2 of distinct buffers
                 gbs = 2 * S / (ms * 1e-3) / 1e9
                 out.append({"kernel": name, "bytes": S, "ms": ms, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                             "frac": gbs / hbm_peak, "unit": "GB/s"})
             del srcs, tables
     else:
         algos = [("oneshot", 1), ("twoshot", 2), ("twoshot_tma", 3)] + ([("nvls", 4)] if comm.has_multicast else [])
-        comm.arena().view(torch.float32).uniform_(-1, 1)
+        comm.arena().view(torch.float32).uniform_(-1e-3, 1e-3)
         torch.cuda.synchronize()
         dist.barrier()
         for S in sizes:
@@ -449,43 +491,48 @@ def bucket_sweep(torch, dist, comm_factory, world, rank, dev, hbm_peak, max_mib,
             for name, algo in algos:
                 if name == "oneshot" and S > (16 << 20):
                     continue
-                def fn(i, S=S, algo=algo, name=name):
+
+                def fn(i, S=S, algo=algo, name=name, reps=reps):
                     off = (i % (reps - 1)) * S if name != "oneshot" else 0
                     comm.allreduce(off, off if name != "oneshot" else (reps - 1) * S, S, lib.F32, algo, 0, sp)
-                iters = 20 if S <= (64 << 20) else 8
-                time_launches(fn, 3)
-                dist.barrier()
-                ms = time_launches(fn, iters)
-                t = torch.tensor([ms], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
+
+                ms = time_graph(fn, max(iters_for(S), reps - 1))
                 bus = S * 2 * (world - 1) / world / (ms * 1e-3) / 1e9
                 out.append({"kernel": f"allreduce_{name}", "bytes": S, "ms": ms, "bound": "nvlink", "achieved": bus,
                             "peak": 900.0, "frac": bus / 900.0, "unit": "GB/s (bus)", "algbw": S / (ms * 1e-3) / 1e9})
                 comm.poll_error()
-        # the comparator on the same box: NCCL all_reduce (what stock DDP calls)
+        # the comparator on the same box: NCCL all_reduce (what stock DDP calls), timed the same way
         for S in sizes:
-            buf = torch.empty(S // 4, device=dev).uniform_(-1, 1)
-            for _ in range(3):
-                dist.all_reduce(buf)
-            torch.cuda.synchronize()
-            ts = []
-            for _ in range(10):
+            reps = max(2, min(8, (288 << 20) // S + 1))
+            bufs = [torch.empty(S // 4, device=dev).uniform_(-1e-3, 1e-3) for _ in range(reps)]
+            for b in bufs[:2]:
+                dist.all_reduce(b)
+            method = "cuda graph"
+            try:
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(bufs[0])  # make sure NCCL has used this stream before capture
+                ms = time_graph(lambda i: dist.all_reduce(bufs[i % reps]), iters_for(S))
+            except Exception as exc:  # capture of NCCL can be refused by some builds: time eagerly instead
+                method = f"eager loop ({type(exc).__name__})"
+                torch.cuda.synchronize()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = iters_for(S)
                 a.record()
-                dist.all_reduce(buf)
+                for i in range(n):
+                    dist.all_reduce(bufs[i % reps])
                 b.record()
                 torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b))
-            ms = statistics.median(ts)
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+                ms = a.elapsed_time(b) / n
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
             out.append({"kernel": "nccl_all_reduce (comparator, not ours)", "bytes": S, "ms": ms, "bound": "nvlink",
                         "achieved": S * 2 * (world - 1) / world / (ms * 1e-3) / 1e9, "peak": 900.0, "frac": None,
-                        "unit": "GB/s (bus)"})
+                        "unit": "GB/s (bus)", "timed": method})
+            del bufs
     torch.cuda.synchronize()
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
     comm.destroy()
     return out
 

@@ -926,8 +926,10 @@ int b200ddp_pick_algo(b200ddp_ctx* c, uint64_t nbytes) {
     return forced;
   }
   if (nbytes <= static_cast<uint64_t>(c->oneshot_max_bytes)) return B200DDP_ALGO_ONESHOT;
-  if (c->has_mc) return B200DDP_ALGO_NVLS;
-  return B200DDP_ALGO_TWOSHOT;
+  // NVLS moves (1 + 1/ws) S per GPU and direction, the peer-to-peer two-shot 2 (ws-1)/ws S: the switch
+  // reduction only pays from ws >= 4 (measured at ws = 2: 393 vs 642 GB/s bus at 256 MiB)
+  if (c->has_mc && c->world >= env_int("B200DDP_NVLS_MIN_WORLD", 4)) return B200DDP_ALGO_NVLS;
+  return B200DDP_ALGO_TWOSHOT_TMA;
 }
 
 int b200ddp_allreduce(b200ddp_ctx* c, uint64_t in_off, uint64_t out_off, uint64_t nbytes, int dtype, int algo,
