@@ -61,7 +61,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "nccl"],
+                    help="b200: this repo; reference: the reference stack on the host cores (gloo/CPU); "
+                         "nccl: stock torch-DDP over NCCL on the same GPUs (comparator, same loop)")
     ap.add_argument("--workload", default=os.environ.get("B200DDP_BENCH_WORKLOAD", "toy"), choices=sorted(WORKLOAD_DESC))
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto: on for the launch-bound toy workload)")
@@ -257,10 +259,19 @@ def main_b200(args):
             x, y = wl.batch(bsz, torch.device("cpu"), gen)
             host_batches.append((x.pin_memory(), y.pin_memory()))
     n_host_batches = len(host_batches)
+    stock = args.impl == "nccl"
+    if stock:  # comparator: the reference's own binding of the name DDP (ref:multigpu_torchrun.py:7)
+        multigpu_torchrun.DDP = torch.nn.parallel.DistributedDataParallel
     trainer = multigpu_torchrun.Trainer(model, host_batches, optimizer, save_every=10**9,
                                         snapshot_path="/nonexistent/snapshot.pt")
     ddp = trainer.model
-    comm = ddp.engine.comm
+
+    class _NoComm:  # stock DDP has no b200ddp communicator
+        launch_count = 0
+        mem_mode = "nccl"
+        has_multicast = None
+
+    comm = _NoComm() if stock else ddp.engine.comm
     dev_batches = [(x.to(dev), y.to(dev)) for x, y in host_batches[: min(len(host_batches), 256)]]
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
 
@@ -275,7 +286,7 @@ def main_b200(args):
         return float(t.item())
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------------
-    use_graph = args.graph == "on" or (args.graph == "auto" and args.workload == "toy")
+    use_graph = (args.graph == "on" or (args.graph == "auto" and args.workload == "toy")) and not stock
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed_steps(n):
@@ -329,6 +340,15 @@ def main_b200(args):
     e2e = {"value": bsz * world * e2e_steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps}
 
+    if stock:
+        if rank == 0:
+            emit({"impl": "nccl", "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+                  "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
+                  "scaling": "weak", "data": "synthetic", "e2e": e2e, "clocks": clock_info,
+                  "config": {"workload": WORKLOAD_DESC[args.workload], "global_batch": bsz * world,
+                             "parallelism": f"dp{world} (stock torch-DDP + NCCL, comparator)"}})
+        dist.destroy_process_group()
+        return 0
     # ---- roofline of the step's dominant kernel: per-launch events on the launching stream -------------
     roof_steps = min(steps, 200)
     trainer._graph = None  # the per-launch events need eager launches of the same kernels
@@ -430,7 +450,7 @@ def bucket_sweep(torch, dist, comm_factory, world, rank, dev, hbm_peak, max_mib,
         sizes = [256 << 10] + sizes
     biggest = max(sizes)
     slots = max(2, (288 << 20) // biggest + 1)  # rotate through >= 288 MiB of distinct arena
-    arena = biggest * slots + (8 << 20) if world > 1 else 2 * biggest + (8 << 20)
+    arena = biggest * slots + (8 << 20)
     comm = comm_factory(arena)
     stream = torch.cuda.Stream(device=dev)
     sp = stream.cuda_stream
@@ -474,8 +494,11 @@ def bucket_sweep(torch, dist, comm_factory, world, rank, dev, hbm_peak, max_mib,
             srcs = [[torch.rand(per, device=dev) for _ in range(n_t)] for _ in range(reps)]
             offs = [i * per for i in range(n_t)]
             tables = [TensorTable([t.data_ptr() for t in ts], offs, [per] * n_t) for ts in srcs]
-            for name, fn in (("flatten_scale", lambda i: comm.flatten_scale(tables[i % reps], lib.F32, 0, 0.5, sp)),
-                             ("unflatten", lambda i: comm.unflatten(tables[i % reps], lib.F32, 0, sp))):
+            # both the gradient side and the bucket side rotate through > L2 of distinct memory
+            for name, fn in (("flatten_scale", lambda i: comm.flatten_scale(tables[i % reps], lib.F32,
+                                                                             (i % (reps - 1)) * S, 0.5, sp)),
+                             ("unflatten", lambda i: comm.unflatten(tables[i % reps], lib.F32,
+                                                                     (i % (reps - 1)) * S, sp))):
                 ms = time_graph(fn, max(iters_for(S), reps))  # one replay streams > L2 of distinct buffers
                 gbs = 2 * S / (ms * 1e-3) / 1e9
                 out.append({"kernel": name, "bytes": S, "ms": ms, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
