@@ -111,12 +111,13 @@ def layout_bucket(index: int, param_indices: Sequence[int], numels: Sequence[int
 
 
 class BucketLayout:
-    """Assigns arena regions to buckets.  One-shot (out-of-place) buckets get an in and an out region."""
+    """Assigns arena regions to buckets from ``start`` on.  Out-of-place (one-shot) and fused (double
+    buffered) buckets get two consecutive regions."""
 
     REGION_ALIGN = 4096
 
-    def __init__(self) -> None:
-        self.total_bytes = 0
+    def __init__(self, start: int = 0) -> None:
+        self.total_bytes = _round_up(int(start), self.REGION_ALIGN)
 
     def place(self, spec: BucketSpec, out_of_place: bool) -> None:
         spec.arena_off = self.total_bytes

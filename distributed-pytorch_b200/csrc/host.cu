@@ -175,7 +175,7 @@ struct b200ddp_ctx {
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::string err;
-  int oneshot_max_bytes = 512 << 10;
+  int oneshot_max_bytes = 0;  // AUTO never picks the one-shot kernel unless B200DDP_ONESHOT_MAX says so
 };
 
 namespace {
@@ -989,7 +989,8 @@ int b200ddp_fused_bucket(b200ddp_ctx* c, void* const* grad_ptrs, const uint64_t*
     return fail(c, B200DDP_EINVAL, "fused_bucket takes 1..%d tensors (got %d)", kMaxTableTensors, n);
   if (bucket_bytes > kFusedMaxBytes)
     return fail(c, B200DDP_EINVAL, "fused_bucket takes at most %llu bytes", (unsigned long long)kFusedMaxBytes);
-  if ((rc = check_range(c, "fused_bucket", bucket_off, bucket_bytes))) return rc;
+  // world > 1: the staging is double buffered, the bucket occupies two slots of bucket_bytes
+  if ((rc = check_range(c, "fused_bucket", bucket_off, bucket_bytes * (c->world > 1 ? 2 : 1)))) return rc;
   TensorTable tt;
   uint32_t vb, ve;
   rc = build_table(c, const_cast<const void* const*>(grad_ptrs), off_el, len_el, 0, n, esize, &tt, &vb, &ve);

@@ -24,6 +24,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace b200ddp {
@@ -174,19 +176,27 @@ __device__ __forceinline__ void write_epoch(const PeerTable& pt, const Ctl& ctl,
 }
 
 // Every thread of the CTA calls this.  On return all CTAs with this blockIdx on all ranks have arrived
-// with `target`, and their prior writes (local and peer) are visible to this CTA.
+// with `target`, and the writes (local and peer) every thread of those CTAs made before arriving are
+// visible to this CTA.  Ordering: the CTA's writes happen-before the bar.sync, the per-peer thread's
+// st.release.sys is cumulative over them (PTX memory model, causality order through the CTA barrier), the
+// waiter's ld.acquire.sys + bar.sync extends that to every thread here — the same pattern as the
+// block barriers of NCCL's and TensorRT-LLM's one/two-shot kernels.
 __device__ __forceinline__ void cta_barrier(const PeerTable& pt, const Ctl& ctl, int ws, uint32_t target) {
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x < ws) {
     const int q = threadIdx.x;
     st_release_sys(flag_slot(pt.base[q], blockIdx.x, ctl.rank), target);
     const uint32_t* mine = flag_slot(pt.base[ctl.rank], blockIdx.x, q);
-    const uint64_t t0 = globaltimer_ns();
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
     while (static_cast<int32_t>(ld_acquire_sys(mine) - target) < 0) {
-      if (globaltimer_ns() - t0 > ctl.timeout_ns) {
-        *reinterpret_cast<volatile uint32_t*>(ctl.err) = 1u + static_cast<uint32_t>(q);
-        break;
+      if ((++spins & 255u) == 0) {  // the timer is only consulted every 256 polls
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > ctl.timeout_ns) {
+          *reinterpret_cast<volatile uint32_t*>(ctl.err) = 1u + static_cast<uint32_t>(q);
+          break;
+        }
       }
     }
   }
@@ -567,9 +577,7 @@ __device__ __forceinline__ void multimem_st(void* p, const uint4& v) {
                : "memory");
 }
 
-constexpr int kNvlsUnroll = 4;
-
-template <int DT>
+template <int DT, int kNvlsUnroll>
 __global__ void __launch_bounds__(kArThreads)
 nvls_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t mc_base, uint64_t in_off,
             uint64_t out_off, uint64_t nvec) {
@@ -604,6 +612,9 @@ nvls_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ct
 // CTA b owns bucket vectors [b*kFusedVecPerCta, ...): it gathers them from the gradients into its own
 // arena, meets CTA b of every peer, sums the same range of all arenas and scatters the result straight
 // back into the gradients from registers.
+// The arena staging is DOUBLE BUFFERED (slot = bit 1 of the CTA's barrier generation), which removes the
+// trailing barrier: a slot is only rewritten two generations later, and passing the start barrier of the
+// generation in between proves every peer has finished reading it.  One NVLink round trip per bucket.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kFusedThreads = 256;
 constexpr uint32_t kFusedVecPerCta = 1024;
@@ -617,8 +628,8 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
   const int n = tt.n;
   const uint32_t v_begin = blockIdx.x * kFusedVecPerCta;
   const uint32_t v_end = min(nvec, v_begin + kFusedVecPerCta);
-  uint4* mine = reinterpret_cast<uint4*>(arena_of(pt, ctl.rank) + bucket_off);
   if (WS == 1) {
+    uint4* mine = reinterpret_cast<uint4*>(arena_of(pt, ctl.rank) + bucket_off);
     for (uint32_t v = v_begin + threadIdx.x; v < v_end; v += kFusedThreads) {
       const int t = locate(s.off, 0, n - 1, v);
       const uint4 x = scale_vec<DT>(gather_vec<DT>(s, t, v), scale);
@@ -628,6 +639,8 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
     return;
   }
   const uint32_t e = read_epoch(pt, ctl);
+  const uint64_t slot_off = bucket_off + ((e >> 1) & 1u) * (static_cast<uint64_t>(nvec) * 16);
+  uint4* mine = reinterpret_cast<uint4*>(arena_of(pt, ctl.rank) + slot_off);
   for (uint32_t v = v_begin + threadIdx.x; v < v_end; v += kFusedThreads) {
     const int t = locate(s.off, 0, n - 1, v);
     st_vec(mine + v, scale_vec<DT>(gather_vec<DT>(s, t, v), scale));
@@ -635,7 +648,7 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
   cta_barrier(pt, ctl, WS, e + 1);
   const uint4* in[WS];
 #pragma unroll
-  for (int q = 0; q < WS; ++q) in[q] = reinterpret_cast<const uint4*>(arena_of(pt, q) + bucket_off);
+  for (int q = 0; q < WS; ++q) in[q] = reinterpret_cast<const uint4*>(arena_of(pt, q) + slot_off);
   for (uint32_t v = v_begin + threadIdx.x; v < v_end; v += kFusedThreads) {
     uint4 x[WS];
 #pragma unroll
@@ -643,7 +656,6 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
     const int t = locate(s.off, 0, n - 1, v);
     scatter_vec<DT>(s, t, v, reduce_vecs<DT, WS>(x));
   }
-  cta_barrier(pt, ctl, WS, e + 2);
   write_epoch(pt, ctl, e + 2);
 }
 
@@ -784,9 +796,21 @@ cudaError_t launch_twoshot_tma(const PeerTable& pt, const Ctl& ctl, uint64_t in_
 cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, uint64_t in_off, uint64_t out_off,
                         uint64_t nvec, int dtype, int max_ctas, cudaStream_t s) {
   const uint64_t slice = (nvec + ctl.world - 1) / ctl.world;
-  const uint64_t step = uint64_t(kArThreads) * kNvlsUnroll;
+  static const int unroll = [] {
+    const char* e = getenv("B200DDP_NVLS_UNROLL");
+    const int u = e ? atoi(e) : 4;
+    return (u == 2 || u == 8) ? u : 4;
+  }();
+  const uint64_t step = uint64_t(kArThreads) * unroll;
   const int grid = clamp_grid((slice + step - 1) / step, max_ctas, 36);
-  B200_DISPATCH_DT(dtype, { nvls_kernel<DT><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec); });
+  B200_DISPATCH_DT(dtype, {
+    if (unroll == 2)
+      nvls_kernel<DT, 2><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec);
+    else if (unroll == 8)
+      nvls_kernel<DT, 8><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec);
+    else
+      nvls_kernel<DT, 4><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec);
+  });
   return cudaGetLastError();
 }
 

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .bucketing import DEFAULT_BUCKET_BYTES_CAP, DEFAULT_FIRST_BUCKET_BYTES
-from .reducer import BucketEngine, P2PEngine, Reducer, arena_bytes_for
+from .reducer import BucketEngine, P2PEngine, Reducer, arena_bytes_for, staging_bytes_for
 
 _live_ddp: List["DistributedDataParallel"] = []
 
@@ -90,8 +90,10 @@ class DistributedDataParallel(nn.Module):
 
         state = self._module_states()
         if _engine is None:
-            # the arena also stages the construction-time / per-forward broadcasts
-            self.engine: BucketEngine = P2PEngine(self.device, arena_bytes_for(params))
+            # arena = broadcast staging (construction-time / per-forward sync) + bucket storage
+            staging = staging_bytes_for(state)
+            self.engine: BucketEngine = P2PEngine(self.device, arena_bytes_for(params) + staging,
+                                                  staging_bytes=staging)
         else:
             self.engine = _engine
         self._verify_param_shapes(params)

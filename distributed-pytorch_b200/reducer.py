@@ -71,13 +71,21 @@ class P2PEngine(BucketEngine):
     """The product engine: buckets live in the IPC-shared arena of a ``P2PComm`` and are reduced by the
     sm_100a kernels of libb200ddp.so on a dedicated high-priority side stream."""
 
-    def __init__(self, device: torch.device, arena_bytes: int, comm: Optional[P2PComm] = None) -> None:
+    #: default size of the arena's broadcast staging region when the caller does not size it
+    DEFAULT_STAGING = 1 << 20
+
+    def __init__(self, device: torch.device, arena_bytes: int, comm: Optional[P2PComm] = None,
+                 staging_bytes: Optional[int] = None) -> None:
         if device.type != "cuda":
             raise RuntimeError("b200ddp reduces gradients on B200 GPUs only; module parameters must be on a "
                                f"CUDA device (got {device}) — there is no CPU path")
         self.device = device
         self.comm = comm if comm is not None else P2PComm.from_process_group(arena_bytes, device.index)
         self.rank, self.world_size = self.comm.rank, self.comm.world
+        # arena = [broadcast staging | buckets]: parameter/buffer broadcasts never touch bucket storage, so a
+        # bucket kernel without a trailing barrier (fused path) cannot be overtaken by a staging write
+        self.staging_bytes = (min(self.DEFAULT_STAGING, self.comm.arena_bytes // 4) if staging_bytes is None
+                              else int(staging_bytes)) // 4096 * 4096
         self.scale = 1.0 / self.world_size
         with torch.cuda.device(device):
             self.stream = torch.cuda.Stream(device=device, priority=-1)
@@ -91,17 +99,24 @@ class P2PEngine(BucketEngine):
 
     # ---- planning -----------------------------------------------------------------------------------
     def plan(self, buckets: List[BucketSpec]) -> None:
-        layout = BucketLayout()
+        layout = BucketLayout(start=self.staging_bytes)
+        multi = self.world_size > 1
         for b in buckets:
             b.fused = b.nbytes <= self._fused_max and len(b.param_indices) <= self._max_table
             b.algo = _lib.ALGO_ONESHOT if b.fused else self.comm.pick_algo(b.nbytes)
-            if self.world_size == 1:
+            if not multi:
                 b.algo = _lib.ALGO_AUTO
-            layout.place(b, out_of_place=(not b.fused and b.algo == _lib.ALGO_ONESHOT and self.world_size > 1))
+            # two regions: in/out of the out-of-place one-shot kernel, or the fused kernel's two staging slots
+            layout.place(b, out_of_place=multi and (b.fused or b.algo == _lib.ALGO_ONESHOT))
         if layout.total_bytes > self.comm.arena_bytes:
             raise RuntimeError(f"bucket layout needs {layout.total_bytes} bytes but the arena has "
                                f"{self.comm.arena_bytes}")
         self._tables.clear()
+        if multi:
+            # (re-)laying out the arena is collective: fence it so that no rank writes a new region while a
+            # peer's earlier kernel (old layout) may still read the same bytes
+            self.comm.stream_wait(self._stream_ptr, torch.cuda.current_stream(self.device).cuda_stream)
+            self.comm.barrier(self._stream_ptr)
 
     def _table(self, bucket: BucketSpec, tensors: Sequence[torch.Tensor]) -> TensorTable:
         ptrs = [t.data_ptr() for t in tensors]
@@ -177,7 +192,7 @@ class P2PEngine(BucketEngine):
             nbytes = t.numel() * t.element_size()
             unit = 4 if nbytes % 4 == 0 and t.data_ptr() % 4 == 0 else 2
             groups[unit].append(t)
-        cap = self.comm.arena_bytes
+        cap = self.staging_bytes
         for unit, ts in groups.items():
             code = _lib.F32 if unit == 4 else _lib.BF16
             i = 0
@@ -190,7 +205,8 @@ class P2PEngine(BucketEngine):
                     if chunk and off * unit + padded > cap:
                         break
                     if padded > cap:
-                        raise RuntimeError("tensor larger than the broadcast arena")
+                        raise RuntimeError(f"a {padded}-byte tensor does not fit the {cap}-byte broadcast staging "
+                                           "region of the arena")
                     chunk.append(ts[i]); offs.append(off); lens.append(n_el)
                     off += padded // unit
                     i += 1
@@ -354,6 +370,15 @@ class Reducer:
 
 
 def arena_bytes_for(params: Sequence[torch.nn.Parameter]) -> int:
-    """Arena size that fits any bucketing of ``params`` (in + out region per bucket, region alignment)."""
+    """Bucket storage that fits any bucketing of ``params`` (two regions per bucket, region alignment)."""
     payload = sum((p.numel() * p.element_size() + 15) // 16 * 16 for p in params)
     return 2 * (payload + len(params) * BucketLayout.REGION_ALIGN) + (1 << 20)
+
+
+def staging_bytes_for(tensors: Sequence[torch.Tensor]) -> int:
+    """Broadcast staging region: holds the largest single tensor, at least 1 MiB, at most 64 MiB unless one
+    tensor is larger (broadcasts are chunked through it)."""
+    largest = max((t.numel() * t.element_size() for t in tensors), default=0)
+    total = sum((t.numel() * t.element_size() + 15) // 16 * 16 for t in tensors)
+    want = max(1 << 20, min(total, 64 << 20), largest + 4096)
+    return (want + 4095) // 4096 * 4096

@@ -133,7 +133,9 @@ int b200ddp_allreduce(b200ddp_ctx* ctx, uint64_t in_off, uint64_t out_off, uint6
 
 /* Small-bucket fast path: flatten+scale, one-shot allreduce and unflatten of one bucket in ONE launch
  * (n <= b200ddp_max_table_tensors(), bucket bytes <= b200ddp_fused_max_bytes()).  Equivalent to
- * flatten_scale -> allreduce(ONESHOT) -> unflatten. */
+ * flatten_scale -> allreduce(ONESHOT) -> unflatten.  With world > 1 the arena staging is double buffered so
+ * that the kernel needs a single cross-GPU barrier: the bucket then occupies
+ * [bucket_off, bucket_off + 2 * bucket_bytes). */
 int b200ddp_fused_bucket(b200ddp_ctx* ctx, void* const* grad_ptrs, const uint64_t* off_el,
                          const uint64_t* len_el, int n, int dtype, uint64_t bucket_off,
                          uint64_t bucket_bytes, float scale, void* stream);

@@ -254,6 +254,31 @@ def test_fused_bucket_matches_three_step_oracle(world, dtype):
             assert np.array_equal(_storage(g, dtype), w)
 
 
+def test_fused_bucket_repeated_calls_alternate_staging_slots(world):
+    """The fused kernel has ONE barrier and double-buffered staging: back-to-back calls on the same bucket
+    (different data every time, no host sync in between) must never read a stale or half-written slot."""
+    lens = [20, 1, 1000, 3]
+    offs = ao.padded_offsets(lens, "f32")
+    total = offs[-1] + 4
+    ws = world.ws
+    scale = float(np.float32(1.0) / np.float32(ws))
+    rounds = 6
+    grads = [[[_rand(n, "f32", torch.Generator().manual_seed(1000 * k + 10 * r + i)) for i, n in enumerate(lens)]
+              for r in range(ws)] for k in range(rounds)]
+    wants = [ao.ddp_average([[_storage(g, "f32") for g in gs] for gs in grads[k]]) for k in range(rounds)]
+    for k in range(rounds):  # all rounds enqueued before any synchronisation
+        for r, (c, st) in enumerate(zip(world.comms, world.streams)):
+            c.fused_bucket(TensorTable([g.data_ptr() for g in grads[k][r]], offs, lens), _lib.F32, 16384, total * 4,
+                           scale, st.cuda_stream)
+    torch.cuda.synchronize()
+    for c in world.comms:
+        c.poll_error()
+    for k in range(rounds):
+        for r in range(ws):
+            for g, w in zip(grads[k][r], wants[k]):
+                assert np.array_equal(_storage(g, "f32"), w), f"round {k} rank {r}"
+
+
 def test_broadcast_and_barrier(world):
     n = 4 * 100003
     for root in (0, world.ws - 1):

@@ -140,6 +140,7 @@ def test_bucket_layout_alignment():
     assert spec.offsets_el == [0, 20, 24] and spec.nbytes == 32 * 4
     spec16 = layout_bucket(0, [0, 1], [3, 9], dtype_code=1, elem_size=2)
     assert spec16.offsets_el == [0, 8] and spec16.nbytes == 48
+    assert BucketLayout(start=5000).total_bytes == 8192
     lay = BucketLayout()
     lay.place(spec, out_of_place=True)
     assert spec.arena_off == 0 and spec.out_off == 4096 and lay.total_bytes == 8192
