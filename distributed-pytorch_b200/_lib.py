@@ -41,6 +41,8 @@ SYMBOLS = [
     ("b200ddp_fused_bucket", _i, [_vp, _pp, _pu64, _pu64, _i, _i, _u64, _u64, _f, _vp]),
     ("b200ddp_max_table_tensors", _i, []),
     ("b200ddp_fused_max_bytes", _u64, []),
+    ("b200ddp_fused_region_bytes", _u64, [_vp, _u64]),
+    ("b200ddp_clear", _i, [_vp, _u64, _u64, _vp]),
     ("b200ddp_broadcast", _i, [_vp, _u64, _u64, _i, _i, _vp]),
     ("b200ddp_barrier", _i, [_vp, _vp]),
     ("b200ddp_stream_wait", _i, [_vp, _vp, _vp]),

@@ -119,8 +119,13 @@ class BucketLayout:
     def __init__(self, start: int = 0) -> None:
         self.total_bytes = _round_up(int(start), self.REGION_ALIGN)
 
-    def place(self, spec: BucketSpec, out_of_place: bool) -> None:
+    def place(self, spec: BucketSpec, out_of_place: bool = False, region_bytes: Optional[int] = None) -> None:
+        """``region_bytes``: reserve exactly this much (the fused path's double-buffered / LL region)."""
         spec.arena_off = self.total_bytes
+        if region_bytes is not None:
+            self.total_bytes += _round_up(max(region_bytes, spec.nbytes), self.REGION_ALIGN)
+            spec.out_off = spec.arena_off
+            return
         self.total_bytes += _round_up(spec.nbytes, self.REGION_ALIGN)
         if out_of_place:
             spec.out_off = self.total_bytes

@@ -169,6 +169,12 @@ class P2PComm:
         if rc:
             _lib.check(rc, self._ctx, "broadcast")
 
+    def fused_region_bytes(self, bucket_bytes: int) -> int:
+        return int(self._lib.b200ddp_fused_region_bytes(self._ctx, bucket_bytes))
+
+    def clear(self, off: int, nbytes: int, stream: int) -> None:
+        _lib.check(self._lib.b200ddp_clear(self._ctx, off, nbytes, stream), self._ctx, "clear")
+
     def barrier(self, stream: int) -> None:
         _lib.check(self._lib.b200ddp_barrier(self._ctx, stream), self._ctx, "barrier")
 

@@ -660,6 +660,9 @@ extern "C" {
 
 int b200ddp_abi_version(void) { return B200DDP_ABI_VERSION; }
 int b200ddp_max_table_tensors(void) { return kMaxTableTensors; }
+uint64_t b200ddp_fused_region_bytes(b200ddp_ctx* c, uint64_t bucket_bytes) {
+  return c ? fused_region_bytes((bucket_bytes + 15) / 16 * 16, c->world) : 0;
+}
 uint64_t b200ddp_fused_max_bytes(void) { return kFusedMaxBytes; }
 
 const char* b200ddp_last_error(b200ddp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
@@ -989,8 +992,8 @@ int b200ddp_fused_bucket(b200ddp_ctx* c, void* const* grad_ptrs, const uint64_t*
     return fail(c, B200DDP_EINVAL, "fused_bucket takes 1..%d tensors (got %d)", kMaxTableTensors, n);
   if (bucket_bytes > kFusedMaxBytes)
     return fail(c, B200DDP_EINVAL, "fused_bucket takes at most %llu bytes", (unsigned long long)kFusedMaxBytes);
-  // world > 1: the staging is double buffered, the bucket occupies two slots of bucket_bytes
-  if ((rc = check_range(c, "fused_bucket", bucket_off, bucket_bytes * (c->world > 1 ? 2 : 1)))) return rc;
+  // world > 1: the staging is double buffered (two slots, or the LL protocol's slot sets)
+  if ((rc = check_range(c, "fused_bucket", bucket_off, fused_region_bytes(bucket_bytes, c->world)))) return rc;
   TensorTable tt;
   uint32_t vb, ve;
   rc = build_table(c, const_cast<const void* const*>(grad_ptrs), off_el, len_el, 0, n, esize, &tt, &vb, &ve);
@@ -1013,6 +1016,18 @@ int b200ddp_broadcast(b200ddp_ctx* c, uint64_t off, uint64_t nbytes, int root, i
   DeviceGuard g(c->device);
   RT_CHECK(c, launch_broadcast(c->pt, make_ctl(c), off, nbytes / 16, root, max_ctas, static_cast<cudaStream_t>(stream)));
   c->launches++;
+  return 0;
+}
+
+int b200ddp_clear(b200ddp_ctx* c, uint64_t off, uint64_t nbytes, void* stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if ((rc = check_range(c, "clear", off, nbytes))) return rc;
+  if (nbytes == 0) return 0;
+  DeviceGuard g(c->device);
+  RT_CHECK(c, cudaMemsetAsync(static_cast<unsigned char*>(c->base) + kSignalBytes + off, 0, nbytes,
+                              static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -15,6 +15,14 @@ constexpr int kMaxBlocks = 512;
 constexpr int kMaxTableTensors = 160;
 // Largest bucket the single-launch fused path takes.
 constexpr uint64_t kFusedMaxBytes = 256u << 10;
+// Buckets up to this size use the barrier-free LL protocol inside the fused path (world > 1).
+constexpr uint64_t kLLMaxBytes = 32u << 10;
+// Arena bytes the fused path needs for a bucket of `bucket_bytes` (multiple of 16) in a world of `ws`:
+// ws == 1: the bucket itself; LL: 2 slot sets x ws sources x (bucket_bytes / 4) words x 8 bytes;
+// otherwise two staging slots.
+constexpr uint64_t fused_region_bytes(uint64_t bucket_bytes, int ws) {
+  return ws <= 1 ? bucket_bytes : (bucket_bytes <= kLLMaxBytes ? 4ull * ws * bucket_bytes : 2ull * bucket_bytes);
+}
 
 // Layout of the per-rank signal region that precedes the bucket arena inside the shared allocation.
 //   [0, kFlagBytes)              uint32 flag[kMaxBlocks][kMaxWorld]   written by peers, polled locally

@@ -139,6 +139,9 @@ __device__ __forceinline__ uint4 reduce_vecs(const uint4 (&x)[WS]) {
 
 template <int DT>
 __device__ __forceinline__ uint4 scale_vec(const uint4& x, float scale) {
+  // scale == 1 is a bit-exact pass-through: the same kernels move raw bytes of any dtype (parameter and
+  // buffer broadcast), where a multiply would canonicalise NaN payloads of reinterpreted integers
+  if (scale == 1.0f) return x;
   float f[Vec<DT>::N];
   Vec<DT>::unpack(x, f);
 #pragma unroll
@@ -660,6 +663,114 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------
+// fused tiny bucket, LL protocol (<= kLLMaxBytes): NO barrier at all.  Every 4-byte word of the scaled
+// bucket travels with a 4-byte tag in one 8-byte store (single-copy atomic over NVLink): each rank pushes
+// its words into slot [set][rank] of every peer's LL region and then polls its own slots until all ws
+// tags match, sums in rank order and scatters to the gradients.  Latency = one NVLink write + the poll,
+// instead of barrier + read round trip + barrier.  The tag is the CTA's barrier generation (device
+// memory, monotonically increasing, so stale slots can never match); two alternating slot sets make the
+// rewrite of a slot safe (reaching generation g+2 needs every peer's data of g+1, which a peer only sends
+// after it has consumed generation g).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kLLThreads = 256;
+constexpr uint32_t kLLWordsPerCta = 1024;
+
+__device__ __forceinline__ void st_ll(uint2* p, uint32_t data, uint32_t tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
+
+// bucket word w (4 bytes) of tensor t, read from the tensor's storage and pre-scaled
+template <int DT>
+__device__ __forceinline__ uint32_t gather_word(const SmemTable& s, int t, uint32_t w, float scale) {
+  const uint32_t v = w >> 2, j = w & 3;
+  const uint64_t len = s.len[t];
+  if (Vec<DT>::ESIZE == 4) {
+    const uint64_t e = static_cast<uint64_t>(v - s.off[t]) * 4 + j;
+    if (e >= len) return 0u;
+    const float x = reinterpret_cast<const float*>(s.ptr[t])[e];
+    return __float_as_uint(scale == 1.0f ? x : __fmul_rn(x, scale));
+  } else {
+    const uint64_t e = static_cast<uint64_t>(v - s.off[t]) * 8 + 2 * j;
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(s.ptr[t]);
+    uint32_t bits = 0;
+    if (e < len) bits |= p[e];
+    if (e + 1 < len) bits |= static_cast<uint32_t>(p[e + 1]) << 16;
+    if (scale == 1.0f) return bits;
+    // run the pair through the same unpack / multiply / round-once path as the vector kernels
+    uint4 x = make_uint4(bits, 0, 0, 0);
+    return scale_vec<DT>(x, scale).x;
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ void scatter_word(const SmemTable& s, int t, uint32_t w, uint32_t bits) {
+  const uint32_t v = w >> 2, j = w & 3;
+  const uint64_t len = s.len[t];
+  if (Vec<DT>::ESIZE == 4) {
+    const uint64_t e = static_cast<uint64_t>(v - s.off[t]) * 4 + j;
+    if (e < len) reinterpret_cast<uint32_t*>(s.ptr[t])[e] = bits;
+  } else {
+    const uint64_t e = static_cast<uint64_t>(v - s.off[t]) * 8 + 2 * j;
+    uint16_t* p = reinterpret_cast<uint16_t*>(s.ptr[t]);
+    if (e < len) p[e] = static_cast<uint16_t>(bits);
+    if (e + 1 < len) p[e + 1] = static_cast<uint16_t>(bits >> 16);
+  }
+}
+
+template <int DT, int WS>
+__global__ void __launch_bounds__(kLLThreads)
+fused_ll_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ PeerTable pt,
+                const __grid_constant__ Ctl ctl, uint64_t ll_off, uint32_t nwords, float scale) {
+  __shared__ SmemTable s;
+  const uint32_t e = read_epoch(pt, ctl);  // before the barrier inside load_table: thread 0 rewrites it at the end
+  load_table(s, tt);
+  const int n = tt.n;
+  const uint32_t tag = e + 1;
+  const uint64_t set_base = static_cast<uint64_t>((e >> 1) & 1u) * WS * nwords;  // in uint2 units
+  const uint32_t w_begin = blockIdx.x * kLLWordsPerCta;
+  const uint32_t w_end = min(nwords, w_begin + kLLWordsPerCta);
+  // push: my words -> slot [set][my rank] on every rank (my own included)
+  for (uint32_t w = w_begin + threadIdx.x; w < w_end; w += kLLThreads) {
+    const int t = locate(s.off, 0, n - 1, w >> 2);
+    const uint32_t d = gather_word<DT>(s, t, w, scale);
+    const uint64_t slot = set_base + static_cast<uint64_t>(ctl.rank) * nwords + w;
+#pragma unroll
+    for (int q = 0; q < WS; ++q) st_ll(reinterpret_cast<uint2*>(arena_of(pt, q) + ll_off) + slot, d, tag);
+  }
+  // pull: poll my own slots of every source rank, sum in rank order, scatter
+  const uint2* mine = reinterpret_cast<const uint2*>(arena_of(pt, ctl.rank) + ll_off) + set_base;
+  for (uint32_t w = w_begin + threadIdx.x; w < w_end; w += kLLThreads) {
+    uint4 x[WS];
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+#pragma unroll
+    for (int q = 0; q < WS; ++q) {
+      uint2 r = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
+      while (r.y != tag) {
+        if ((++spins & 255u) == 0) {
+          const uint64_t now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > ctl.timeout_ns) {
+            *reinterpret_cast<volatile uint32_t*>(ctl.err) = 1u + static_cast<uint32_t>(q);
+            break;
+          }
+        }
+        r = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
+      }
+      x[q] = make_uint4(r.x, 0, 0, 0);
+    }
+    const int t = locate(s.off, 0, n - 1, w >> 2);
+    scatter_word<DT>(s, t, w, reduce_vecs<DT, WS>(x).x);
+  }
+  write_epoch(pt, ctl, e + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // broadcast by peer stores, and a bare barrier
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kArThreads)
@@ -823,6 +934,12 @@ cudaError_t launch_fused(const TensorTable& tt, const PeerTable& pt, const Ctl& 
     B200_DISPATCH_DT(dtype, {
       fused_bucket_kernel<DT, 1><<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale);
     });
+  } else if (uint64_t(nvec) * 16 <= kLLMaxBytes) {
+    const uint32_t nwords = nvec * 4;
+    const int ll_grid = static_cast<int>((nwords + kLLWordsPerCta - 1) / kLLWordsPerCta);
+    B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
+                       fused_ll_kernel<DT, WS><<<ll_grid, kLLThreads, 0, s>>>(tt, pt, ctl, bucket_off, nwords, scale);
+                     }));
   } else {
     B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
                        fused_bucket_kernel<DT, WS>

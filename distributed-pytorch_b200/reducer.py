@@ -96,6 +96,7 @@ class P2PEngine(BucketEngine):
         self._fused_max = min(P2PComm.fused_max_bytes(), int(os.environ.get("B200DDP_FUSED_MAX", str(1 << 30))))
         self._max_table = P2PComm.max_table_tensors()
         self._keepalive: List[torch.Tensor] = []
+        self._bcast_plans: Dict[tuple, tuple] = {}
 
     # ---- planning -----------------------------------------------------------------------------------
     def plan(self, buckets: List[BucketSpec]) -> None:
@@ -106,16 +107,22 @@ class P2PEngine(BucketEngine):
             b.algo = _lib.ALGO_ONESHOT if b.fused else self.comm.pick_algo(b.nbytes)
             if not multi:
                 b.algo = _lib.ALGO_AUTO
-            # two regions: in/out of the out-of-place one-shot kernel, or the fused kernel's two staging slots
-            layout.place(b, out_of_place=multi and (b.fused or b.algo == _lib.ALGO_ONESHOT))
+            if b.fused:
+                layout.place(b, region_bytes=self.comm.fused_region_bytes(b.nbytes))
+            else:  # two regions for the out-of-place one-shot kernel
+                layout.place(b, out_of_place=multi and b.algo == _lib.ALGO_ONESHOT)
         if layout.total_bytes > self.comm.arena_bytes:
             raise RuntimeError(f"bucket layout needs {layout.total_bytes} bytes but the arena has "
                                f"{self.comm.arena_bytes}")
         self._tables.clear()
         if multi:
-            # (re-)laying out the arena is collective: fence it so that no rank writes a new region while a
-            # peer's earlier kernel (old layout) may still read the same bytes
             self.comm.stream_wait(self._stream_ptr, torch.cuda.current_stream(self.device).cuda_stream)
+            for b in buckets:  # the fused path's tagged slots must start from zero
+                if b.fused:
+                    self.comm.clear(b.arena_off, self.comm.fused_region_bytes(b.nbytes), self._stream_ptr)
+            # (re-)laying out the arena is collective: fence it so that no rank touches a new region while a
+            # peer's earlier kernel (old layout) may still read the same bytes, and so that every rank's
+            # slots are cleared before any peer pushes into them
             self.comm.barrier(self._stream_ptr)
 
     def _table(self, bucket: BucketSpec, tensors: Sequence[torch.Tensor]) -> TensorTable:
@@ -176,47 +183,62 @@ class P2PEngine(BucketEngine):
         self._order_seq += 1
         return f"b200ddp/order/c{self.comm.uid}/n{self._order_seq}"
 
-    def broadcast_tensors(self, tensors: Sequence[torch.Tensor], root: int = 0) -> None:
-        """Root's tensors -> every rank, staged through the arena in raw 4- or 2-byte elements (bit
-        exact for any dtype); tensors whose byte size is odd go through torch.distributed."""
-        if self.world_size == 1 or not tensors:
-            return
-        comm, s = self.comm, self._stream_ptr
-        cur = torch.cuda.current_stream(self.device).cuda_stream
-        comm.stream_wait(s, cur)
+    def _broadcast_plan(self, tensors: Sequence[torch.Tensor]):
+        """Chunk ``tensors`` into staging-sized multi-tensor tables of raw 4- or 2-byte elements (bit exact
+        for any dtype).  Cached per set of storage addresses: the per-forward buffer sync of a model reuses
+        the same plan every step."""
+        key = tuple(t.data_ptr() for t in tensors)
+        plan = self._bcast_plans.get(key)
+        if plan is not None:
+            return plan
         odd = [t for t in tensors if not t.is_contiguous() or (t.numel() * t.element_size()) % 2]
+        odd_ids = {id(t) for t in odd}
         groups = {4: [], 2: []}
         for t in tensors:
-            if any(t is o for o in odd):
+            if id(t) in odd_ids:
                 continue
             nbytes = t.numel() * t.element_size()
-            unit = 4 if nbytes % 4 == 0 and t.data_ptr() % 4 == 0 else 2
-            groups[unit].append(t)
+            groups[4 if nbytes % 4 == 0 and t.data_ptr() % 4 == 0 else 2].append(t)
         cap = self.staging_bytes
+        chunks = []
         for unit, ts in groups.items():
             code = _lib.F32 if unit == 4 else _lib.BF16
             i = 0
             while i < len(ts):
-                # greedily fill the arena, respecting the table limit
                 chunk, offs, lens, off = [], [], [], 0
                 while i < len(ts) and len(chunk) < self._max_table:
                     n_el = ts[i].numel() * ts[i].element_size() // unit
                     padded = (n_el * unit + 15) // 16 * 16
-                    if chunk and off * unit + padded > cap:
-                        break
                     if padded > cap:
                         raise RuntimeError(f"a {padded}-byte tensor does not fit the {cap}-byte broadcast staging "
                                            "region of the arena")
+                    if chunk and off * unit + padded > cap:
+                        break
                     chunk.append(ts[i]); offs.append(off); lens.append(n_el)
                     off += padded // unit
                     i += 1
-                nbytes = max(off * unit, 16)
-                table = TensorTable([t.data_ptr() for t in chunk], offs, lens)
-                if self.rank == root:
-                    comm.flatten_scale(table, code, 0, 1.0, s)
-                comm.broadcast(0, nbytes, root, s, self.max_ctas)
-                if self.rank != root:
-                    comm.unflatten(table, code, 0, s)
+                chunks.append((code, TensorTable([t.data_ptr() for t in chunk], offs, lens), max(off * unit, 16)))
+        plan = (chunks, odd)
+        if len(self._bcast_plans) > 8:
+            self._bcast_plans.clear()
+        self._bcast_plans[key] = plan
+        return plan
+
+    def broadcast_tensors(self, tensors: Sequence[torch.Tensor], root: int = 0) -> None:
+        """Root's tensors -> every rank through the arena's staging region by peer stores; tensors whose byte
+        size is odd (or that are not contiguous) go through torch.distributed."""
+        if self.world_size == 1 or not tensors:
+            return
+        comm, s = self.comm, self._stream_ptr
+        chunks, odd = self._broadcast_plan(tensors)
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        comm.stream_wait(s, cur)
+        for code, table, nbytes in chunks:
+            if self.rank == root:
+                comm.flatten_scale(table, code, 0, 1.0, s)
+            comm.broadcast(0, nbytes, root, s, self.max_ctas)
+            if self.rank != root:
+                comm.unflatten(table, code, 0, s)
         comm.stream_wait(cur, s)
         if odd:
             import torch.distributed as dist
@@ -370,9 +392,11 @@ class Reducer:
 
 
 def arena_bytes_for(params: Sequence[torch.nn.Parameter]) -> int:
-    """Bucket storage that fits any bucketing of ``params`` (two regions per bucket, region alignment)."""
+    """Bucket storage that fits any bucketing of ``params``: two regions per bucket plus region alignment;
+    tiny buckets on the LL path take 4*ws (<= 32) times their <= 32 KiB size, bounded per parameter."""
     payload = sum((p.numel() * p.element_size() + 15) // 16 * 16 for p in params)
-    return 2 * (payload + len(params) * BucketLayout.REGION_ALIGN) + (1 << 20)
+    ll_extra = sum(32 * min((p.numel() * p.element_size() + 15) // 16 * 16, 32 << 10) for p in params)
+    return 2 * (payload + len(params) * BucketLayout.REGION_ALIGN) + ll_extra + (1 << 20)
 
 
 def staging_bytes_for(tensors: Sequence[torch.Tensor]) -> int:

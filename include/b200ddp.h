@@ -134,13 +134,19 @@ int b200ddp_allreduce(b200ddp_ctx* ctx, uint64_t in_off, uint64_t out_off, uint6
 /* Small-bucket fast path: flatten+scale, one-shot allreduce and unflatten of one bucket in ONE launch
  * (n <= b200ddp_max_table_tensors(), bucket bytes <= b200ddp_fused_max_bytes()).  Equivalent to
  * flatten_scale -> allreduce(ONESHOT) -> unflatten.  With world > 1 the arena staging is double buffered so
- * that the kernel needs a single cross-GPU barrier: the bucket then occupies
- * [bucket_off, bucket_off + 2 * bucket_bytes). */
+ * that the kernel needs a single cross-GPU barrier, and buckets of at most 32 KiB use a barrier-free LL
+ * protocol (4-byte word + 4-byte tag per 8-byte NVLink store): the bucket then occupies
+ * [bucket_off, bucket_off + b200ddp_fused_region_bytes(ctx, bucket_bytes)), which the caller must have
+ * cleared once with b200ddp_clear() before the first use (and after re-using the bytes for anything else). */
 int b200ddp_fused_bucket(b200ddp_ctx* ctx, void* const* grad_ptrs, const uint64_t* off_el,
                          const uint64_t* len_el, int n, int dtype, uint64_t bucket_off,
                          uint64_t bucket_bytes, float scale, void* stream);
 int b200ddp_max_table_tensors(void);
 uint64_t b200ddp_fused_max_bytes(void);
+uint64_t b200ddp_fused_region_bytes(b200ddp_ctx* ctx, uint64_t bucket_bytes);
+
+/* Zero arena[off, off + nbytes) on `stream` (offset and size multiples of 16). */
+int b200ddp_clear(b200ddp_ctx* ctx, uint64_t off, uint64_t nbytes, void* stream);
 
 /* Broadcast `nbytes` (multiple of 16) of arena[off] from rank `root` to arena[off] of every rank by
  * peer stores.  Used for DDP's construction-time parameter sync and per-forward buffer sync

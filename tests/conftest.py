@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+# Loop-back worlds run several ranks' spinning kernels on ONE GPU from many streams.  With the default 8
+# hardware work queues two of those streams can share a queue, which serialises a kernel behind the very
+# kernel that waits for it.  (One process per GPU — the product configuration — uses 2 streams.)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 
 

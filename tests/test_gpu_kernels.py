@@ -69,6 +69,31 @@ def test_flatten_unflatten_bit_exact(comm1, dtype, scale):
     comm1.poll_error()
 
 
+def test_scale_one_is_bitwise_passthrough(comm1):
+    """scale == 1 moves raw bytes (parameter/buffer broadcast of any dtype): NaN payloads, signalling NaNs,
+    denormals and reinterpreted integers must survive flatten and unflatten bit for bit."""
+    pats = torch.tensor([-1, 0x7F800001, 0x7FC12345, 0x00000001, -2147483648, 0x7F7FFFFF, 1234567, 0, 5],
+                        dtype=torch.int64).to(torch.int32).cuda()
+    big = torch.randint(-2**31, 2**31 - 1, (4096 * 3 + 1,), dtype=torch.int64).to(torch.int32).cuda()
+    srcs = [pats, big]
+    lens = [t.numel() for t in srcs]
+    offs = ao.padded_offsets(lens, "f32")
+    s = torch.cuda.current_stream().cuda_stream
+    comm1.flatten_scale(TensorTable([t.data_ptr() for t in srcs], offs, lens), _lib.F32, 0, 1.0, s)
+    outs = [torch.zeros_like(t) for t in srcs]
+    comm1.unflatten(TensorTable([t.data_ptr() for t in outs], offs, lens), _lib.F32, 0, s)
+    torch.cuda.synchronize()
+    for a, b in zip(srcs, outs):
+        assert torch.equal(a, b)
+    # 16-bit raw path
+    h = torch.randint(-32768, 32767, (1001,), dtype=torch.int16).cuda()
+    o = torch.zeros_like(h)
+    comm1.flatten_scale(TensorTable([h.data_ptr()], [0], [1001]), _lib.BF16, 0, 1.0, s)
+    comm1.unflatten(TensorTable([o.data_ptr()], [0], [1001]), _lib.BF16, 0, s)
+    torch.cuda.synchronize()
+    assert torch.equal(h, o)
+
+
 def test_flatten_unaligned_sources_and_many_tiny_tensors(comm1):
     """Storage offsets that break 16-byte alignment, and > one table (160) of tiny tensors (ResNet-50 has
     107 gradients below 16 KiB)."""
@@ -233,9 +258,10 @@ def test_linearity_at_full_bucket_size(world):
         assert torch.equal(c.view(0, nbytes, torch.float32), expect)
 
 
-@pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_fused_bucket_matches_three_step_oracle(world, dtype):
-    lens = [20, 1, 300, 7, 4096, 1]
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("lens", [[20, 1], [20, 1, 300, 7, 4096, 1], [3, 9001, 5, 20000, 2]],
+                         ids=["toy84B-LL", "17KB-LL", "116KB-barrier"])
+def test_fused_bucket_matches_three_step_oracle(world, dtype, lens):
     offs = ao.padded_offsets(lens, dtype)
     epv = 16 // ao.elem_size(dtype)
     total = offs[-1] + epv
@@ -247,17 +273,21 @@ def test_fused_bucket_matches_three_step_oracle(world, dtype):
         gen = torch.Generator().manual_seed(50 + r)
         grads.append([_rand(n, dtype, gen) for n in lens])
     want = ao.ddp_average([[_storage(g, dtype) for g in gs] for gs in grads], dtype)
+    region = world.comms[0].fused_region_bytes(nbytes)
+    assert region == (4 * ws * nbytes if nbytes <= 32768 else 2 * nbytes)
+    world.run(lambda r, c, s: c.clear(1 << 20, region, s))  # tagged slots start from zero
     world.run(lambda r, c, s: c.fused_bucket(TensorTable([g.data_ptr() for g in grads[r]], offs, lens),
-                                             DT[dtype][1], 8192, nbytes, scale, s))
+                                             DT[dtype][1], 1 << 20, nbytes, scale, s))
     for r in range(ws):
         for g, w in zip(grads[r], want):
             assert np.array_equal(_storage(g, dtype), w)
 
 
-def test_fused_bucket_repeated_calls_alternate_staging_slots(world):
-    """The fused kernel has ONE barrier and double-buffered staging: back-to-back calls on the same bucket
-    (different data every time, no host sync in between) must never read a stale or half-written slot."""
-    lens = [20, 1, 1000, 3]
+@pytest.mark.parametrize("lens", [[20, 1, 1000, 3], [20, 1, 9000, 3]], ids=["LL", "barrier"])
+def test_fused_bucket_repeated_calls_alternate_staging_slots(world, lens):
+    """The fused kernels have at most ONE barrier (none on the LL path) and double-buffered staging:
+    back-to-back calls on the same bucket (different data every time, no host sync in between) must never
+    read a stale or half-written slot."""
     offs = ao.padded_offsets(lens, "f32")
     total = offs[-1] + 4
     ws = world.ws
@@ -266,6 +296,7 @@ def test_fused_bucket_repeated_calls_alternate_staging_slots(world):
     grads = [[[_rand(n, "f32", torch.Generator().manual_seed(1000 * k + 10 * r + i)) for i, n in enumerate(lens)]
               for r in range(ws)] for k in range(rounds)]
     wants = [ao.ddp_average([[_storage(g, "f32") for g in gs] for gs in grads[k]]) for k in range(rounds)]
+    world.run(lambda r, c, s: c.clear(16384, c.fused_region_bytes(total * 4), s))
     for k in range(rounds):  # all rounds enqueued before any synchronisation
         for r, (c, st) in enumerate(zip(world.comms, world.streams)):
             c.fused_bucket(TensorTable([g.data_ptr() for g in grads[k][r]], offs, lens), _lib.F32, 16384, total * 4,
