@@ -738,7 +738,7 @@ int b200ddp_init(int rank, int world, int device, uint64_t arena_bytes, int mem_
   }
   *c->err_host = 0;
   if (cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming) != cudaSuccess ||
-      prepare_kernels() != cudaSuccess) {
+      prepare_kernels(world) != cudaSuccess) {
     fail(c, B200DDP_ECUDA, "kernel/event setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     return bail(B200DDP_ECUDA);
   }

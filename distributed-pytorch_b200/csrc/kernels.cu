@@ -962,29 +962,61 @@ cudaError_t launch_barrier(const PeerTable& pt, const Ctl& ctl, cudaStream_t s) 
 }
 
 namespace {
-template <int DT, int WS>
-cudaError_t opt_in_tma() {
-  constexpr int smem = tma_stages(WS) * WS * kTmaChunkBytes;
-  return cudaFuncSetAttribute(twoshot_tma_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+// CUDA loads kernels lazily, on first launch, and a load cannot complete while another kernel is still
+// running on the device.  A kernel that spins for a peer must therefore never be the reason a peer-side
+// launch is stuck behind a pending load (it deadlocks a single-GPU loop-back world outright, and is a
+// needless serialisation point otherwise): every kernel this world size can launch is loaded up front.
+template <typename K>
+cudaError_t preload(K kernel) {
+  cudaFuncAttributes attr;
+  return cudaFuncGetAttributes(&attr, kernel);
 }
-template <int DT>
-cudaError_t opt_in_tma_all_ws() {
+
+template <int DT, int WS>
+cudaError_t prepare_ws() {
   cudaError_t e;
-  if ((e = opt_in_tma<DT, 2>()) != cudaSuccess) return e;
-  if ((e = opt_in_tma<DT, 3>()) != cudaSuccess) return e;
-  if ((e = opt_in_tma<DT, 4>()) != cudaSuccess) return e;
-  if ((e = opt_in_tma<DT, 5>()) != cudaSuccess) return e;
-  if ((e = opt_in_tma<DT, 6>()) != cudaSuccess) return e;
-  if ((e = opt_in_tma<DT, 7>()) != cudaSuccess) return e;
-  return opt_in_tma<DT, 8>();
+  constexpr int smem = tma_stages(WS) * WS * kTmaChunkBytes;
+  if ((e = cudaFuncSetAttribute(twoshot_tma_kernel<DT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) !=
+      cudaSuccess)
+    return e;
+  if ((e = preload(twoshot_tma_kernel<DT, WS>)) != cudaSuccess) return e;
+  if ((e = preload(oneshot_kernel<DT, WS>)) != cudaSuccess) return e;
+  if ((e = preload(twoshot_kernel<DT, WS>)) != cudaSuccess) return e;
+  if ((e = preload(fused_bucket_kernel<DT, WS>)) != cudaSuccess) return e;
+  return preload(fused_ll_kernel<DT, WS>);
+}
+
+template <int DT>
+cudaError_t prepare_dt(int world) {
+  cudaError_t e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, false>)) != cudaSuccess) return e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, true>)) != cudaSuccess) return e;
+  if ((e = preload(fused_bucket_kernel<DT, 1>)) != cudaSuccess) return e;
+  if ((e = preload(nvls_kernel<DT, 2>)) != cudaSuccess) return e;
+  if ((e = preload(nvls_kernel<DT, 4>)) != cudaSuccess) return e;
+  if ((e = preload(nvls_kernel<DT, 8>)) != cudaSuccess) return e;
+  switch (world) {
+    case 1: return cudaSuccess;
+    case 2: return prepare_ws<DT, 2>();
+    case 3: return prepare_ws<DT, 3>();
+    case 4: return prepare_ws<DT, 4>();
+    case 5: return prepare_ws<DT, 5>();
+    case 6: return prepare_ws<DT, 6>();
+    case 7: return prepare_ws<DT, 7>();
+    case 8: return prepare_ws<DT, 8>();
+    default: return cudaErrorInvalidValue;
+  }
 }
 }  // namespace
 
-cudaError_t prepare_kernels() {
+cudaError_t prepare_kernels(int world) {
   cudaError_t e;
-  if ((e = opt_in_tma_all_ws<B200DDP_F32>()) != cudaSuccess) return e;
-  if ((e = opt_in_tma_all_ws<B200DDP_BF16>()) != cudaSuccess) return e;
-  return opt_in_tma_all_ws<B200DDP_F16>();
+  if ((e = preload(local_copy_kernel)) != cudaSuccess) return e;
+  if ((e = preload(broadcast_kernel)) != cudaSuccess) return e;
+  if ((e = preload(barrier_kernel)) != cudaSuccess) return e;
+  if ((e = prepare_dt<B200DDP_F32>(world)) != cudaSuccess) return e;
+  if ((e = prepare_dt<B200DDP_BF16>(world)) != cudaSuccess) return e;
+  return prepare_dt<B200DDP_F16>(world);
 }
 
 }  // namespace b200ddp

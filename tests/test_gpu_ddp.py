@@ -141,6 +141,11 @@ def test_loopback_ws2_replays_reference_trainer():
 
     fx = torch.load(os.path.join(GOLD, "ref_trainer_ws2.pt"))["cases"]["mse"]
     dev = torch.device("cuda", 0)
+    # stage every batch on the GPU first: in a loop-back world ONE host thread drives both ranks, so it must
+    # never block (pageable H2D copies, allocator growth) between launching rank 0's kernel and rank 1's
+    xs = [[fx[r]["x"][s].cuda() for s in range(4)] for r in range(2)]
+    ys = [[fx[r]["y"][s].cuda() for s in range(4)] for r in range(2)]
+    torch.cuda.synchronize()
     comms = P2PComm.loopback_world(2, 0, 8 << 20)
     for c in comms:
         c.set_timeout_ms(10000)
@@ -163,9 +168,8 @@ def test_loopback_ws2_replays_reference_trainer():
     for step in range(4):
         for r in range(2):
             with torch.cuda.stream(streams[r]):
-                x, y = fx[r]["x"][step].cuda(), fx[r]["y"][step].cuda()
                 opts[r].zero_grad()
-                torch.nn.functional.mse_loss(ddps[r](x), y).backward()
+                torch.nn.functional.mse_loss(ddps[r](xs[r][step]), ys[r][step]).backward()
         torch.cuda.synchronize()
         per_rank = [[g.numpy() for g in fx[r]["local_grads"][step]] for r in range(2)]
         oracle = ao.ddp_average(per_rank)
