@@ -80,8 +80,29 @@ def main():
                 rows.append(row)
                 if rank == 0:
                     print(json.dumps(row), flush=True)
+    # the fused single-launch path (flatten+scale -> allreduce -> unflatten): LL protocol <= 32 KiB, one barrier above
+    from b200ddp.comm import TensorTable
+
+    for kib in [float(x) for x in kw.get("fused_kib", "0.09375,4,16,32,64,256").split(",") if x]:
+        n_el = max(4, int(kib * 1024) // 4 // 4 * 4)
+        nbytes = n_el * 4
+        g = torch.rand(n_el, device=dev)
+        table = TensorTable([g.data_ptr()], [0], [n_el])
+        region = comm.fused_region_bytes(nbytes)
+        comm.clear(0, region, sp)
+        stream.synchronize()
+        dist.barrier()
+        ms = time_graph(lambda i: comm.fused_bucket(table, code if dt == "f32" else _lib.F32, 0, nbytes, 1.0 / world, sp), 50)
+        comm.poll_error()
+        row = dict(algo="fused_ll" if nbytes <= 32768 else "fused_1barrier", mib=nbytes / (1 << 20), ctas=0, us=ms * 1e3,
+                   bus_gbs=nbytes * 2 * (world - 1) / world / (ms * 1e-3) / 1e9, world=world, dtype="f32")
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+    comm.arena().view(torch.float32).uniform_(-1e-3, 1e-3)
+    torch.cuda.synchronize()
+    dist.barrier()
     # NCCL on the same box, same timing method
-    for S in sizes:
+    for S in (sizes if kw.get("nccl", "1") == "1" else []):
         reps = max(2, min(8, (288 << 20) // S + 1))
         bufs = [torch.empty(S // 4, device=dev).uniform_(-1e-3, 1e-3) for _ in range(reps)]
         with torch.cuda.stream(stream):
