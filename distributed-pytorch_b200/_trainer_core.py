@@ -81,4 +81,7 @@ class TrainerCore:
         first = next(iter(self.train_data))[0]
         print(f"[GPU{self.gpu_id}] Epoch {epoch} | Batchsize: {len(first)} | Steps: {steps}")
         for source, targets in self.train_data:
-            self._run_batch(source.to(self.gpu_id), targets.to(self.gpu_id))
+            if self._graph is not None:  # the replayed step copies host batches straight into its input buffers
+                self._run_batch(source, targets)
+            else:
+                self._run_batch(source.to(self.gpu_id), targets.to(self.gpu_id))

@@ -913,7 +913,10 @@ cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, u
     return (u == 2 || u == 8) ? u : 4;
   }();
   const uint64_t step = uint64_t(kArThreads) * unroll;
-  const int grid = clamp_grid((slice + step - 1) / step, max_ctas, 36);
+  // measured on 8x B200 (profiles/r01_allreduce_sweep.md): 8 CTAs x 512 threads x 4 vectors in flight is
+  // the sweet spot at every size (more CTAs only add contention at the switch), and leaves 140 SMs to
+  // the backward
+  const int grid = clamp_grid((slice + step - 1) / step, max_ctas, 8);
   B200_DISPATCH_DT(dtype, {
     if (unroll == 2)
       nvls_kernel<DT, 2><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec);

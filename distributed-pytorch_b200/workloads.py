@@ -121,6 +121,10 @@ WORKLOADS = {
     "slices": Workload("slices", lambda: SliceHeads(64, 4096, 64), _rows(4096, 64), F.mse_loss),
     "resnet50": Workload("resnet50", _resnet50, _images, F.cross_entropy),
     "gpt2m": Workload("gpt2m", lambda: GPT2Shaped().to(torch.bfloat16), _tokens, _lm_loss, torch.bfloat16, 8),
+    "mlp_bf16": Workload("mlp_bf16", lambda: nn.Sequential(nn.Linear(20, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(),
+                                                           nn.Linear(256, 7)).to(torch.bfloat16),
+                         lambda b, device, gen=None: tuple(t.to(torch.bfloat16) for t in _rows(20, 7)(b, device, gen)),
+                         F.mse_loss, torch.bfloat16),
     # small multi-bucket model for parity tests
     "mlp": Workload("mlp", lambda: nn.Sequential(nn.Linear(20, 96), nn.ReLU(), nn.Linear(96, 96), nn.ReLU(),
                                                  nn.Linear(96, 7)), _rows(20, 7), F.mse_loss),

@@ -293,12 +293,15 @@ def test_multigpu_raw_allreduce_all_algorithms(mem):
 
 @needs_multi
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("workload", ["mlp", "slices"])
+@pytest.mark.parametrize("workload", ["mlp", "slices", "mlp_bf16"])
 def test_multigpu_ddp_matches_stock_nccl_ddp(workload):
     """mlp: fused small buckets; slices: 64 MiB of gradients in 1 MiB + 25 MiB buckets (one-shot and the
     large-bucket algorithm AUTO picks, NVLS when the fabric has it)."""
     world = min(torch.cuda.device_count(), 8)
     out = _spawn_mp("ddp_vs_nccl", world, workload=workload)
+    # fp32: north_star's 1e-6 rel.  bf16 storage: we accumulate in fp32 and round once, NCCL sums in bf16 —
+    # both end on the bf16 grid, so they differ by at most a couple of bf16 ulps (2^-8 relative each)
+    tol = 2e-2 if workload.endswith("bf16") else 1e-6
     for r in range(world):
-        assert out[r]["worst_rel"] <= 1e-6, out[r]
+        assert out[r]["worst_rel"] <= tol, out[r]
         assert out[r]["weights_equal_across_ranks"]
