@@ -913,10 +913,12 @@ cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, u
     return (u == 2 || u == 8) ? u : 4;
   }();
   const uint64_t step = uint64_t(kArThreads) * unroll;
-  // measured on 8x B200 (profiles/r01_allreduce_sweep.md): 8 CTAs x 512 threads x 4 vectors in flight is
-  // the sweet spot at every size (more CTAs only add contention at the switch), and leaves 140 SMs to
-  // the backward
-  const int grid = clamp_grid((slice + step - 1) / step, max_ctas, 8);
+  // measured (profiles/r01_allreduce_sweep.md): at ws = 8, 8 CTAs x 512 threads x 4 vectors in flight is the
+  // sweet spot at every size (more CTAs only add contention at the switch) and leaves 140 SMs to the
+  // backward; a rank's slice is S/ws, so smaller worlds get proportionally more CTAs (ws = 2: 8 CTAs
+  // measured 210 GB/s against 393 GB/s with 36)
+  const int dflt = ctl.world >= 8 ? 8 : (ctl.world >= 4 ? 16 : 36);
+  const int grid = clamp_grid((slice + step - 1) / step, max_ctas, dflt);
   B200_DISPATCH_DT(dtype, {
     if (unroll == 2)
       nvls_kernel<DT, 2><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec);
