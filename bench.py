@@ -246,13 +246,16 @@ def main_b200(args):
         # does (ref:multigpu.py:72-79), collated into pinned batches of 32
         from torch.utils.data.distributed import DistributedSampler
 
-        from b200ddp.utils import MyTrainDataset
+        from b200ddp.utils import DeviceShardLoader, MyTrainDataset
 
         ds = MyTrainDataset(32768, seed=1234)
-        idx = torch.tensor(list(DistributedSampler(ds)), dtype=torch.long)
+        sampler = DistributedSampler(ds)
+        idx = torch.tensor(list(sampler), dtype=torch.long)
         for i in range(0, len(idx) - bsz + 1, bsz):
             sel = idx[i:i + bsz]
             host_batches.append((ds.x[sel].pin_memory(), ds.y[sel].pin_memory()))
+        # the HBM-resident leg reads the same shard through the device-resident loader
+        shard_loader = DeviceShardLoader(ds, bsz, torch.device("cuda", local), sampler=sampler)
     else:
         gen = torch.Generator().manual_seed(4321 + rank)
         for _ in range(8):
@@ -272,7 +275,10 @@ def main_b200(args):
         has_multicast = None
 
     comm = _NoComm() if stock else ddp.engine.comm
-    dev_batches = [(x.to(dev), y.to(dev)) for x, y in host_batches[: min(len(host_batches), 256)]]
+    if args.workload == "toy":
+        dev_batches = [(x, y) for x, y in shard_loader if x.shape[0] == bsz][:256]
+    else:
+        dev_batches = [(x.to(dev), y.to(dev)) for x, y in host_batches[: min(len(host_batches), 256)]]
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
 
     def barrier_sync():

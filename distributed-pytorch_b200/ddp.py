@@ -102,6 +102,7 @@ class DistributedDataParallel(nn.Module):
         self.engine.broadcast_tensors(state, root=0)
         self.reducer = Reducer(params, self.engine, cap, first)
         self.require_backward_grad_sync = True
+        self.require_forward_param_sync = True
         _live_ddp.append(self)
 
     # ---- construction helpers ------------------------------------------------------------------------
@@ -135,18 +136,23 @@ class DistributedDataParallel(nn.Module):
     def forward(self, *inputs: Any, **kwargs: Any) -> Any:
         if self.device_ids is not None:
             inputs, kwargs = _move(inputs, self.device), _move(kwargs, self.device)
-        will_sync = torch.is_grad_enabled() and self.require_backward_grad_sync
-        if self.broadcast_buffers and will_sync:
-            buffers = [b for b in self.module.buffers()]
+        if self.require_forward_param_sync and self.broadcast_buffers:
+            # rank 0's buffers before the forward (will_sync_module_buffers / _sync_buffers,
+            # torch:nn/parallel/distributed.py:1590-1591,2191-2196,2214-2256).  As in torch, the flag is what
+            # the PREVIOUS forward left behind: buffers are synchronised before a forward iff the forward
+            # before it was a gradient-synchronising one (:1637-1650)
+            buffers = [b.detach() for b in self.module.buffers()]
             if buffers:
-                # torch:nn/parallel/distributed.py:1590-1591,2214-2256: rank 0's buffers before forward
-                self.engine.broadcast_tensors([b.detach() for b in buffers], root=0)
+                self.engine.broadcast_tensors(buffers, root=0)
         out = self.module(*inputs, **kwargs)
-        if torch.is_grad_enabled():
-            self.reducer.require_sync = self.require_backward_grad_sync
-            if self.require_backward_grad_sync:
-                self.reducer.prepare_for_backward()
-            else:
+        if torch.is_grad_enabled() and self.require_backward_grad_sync:
+            self.require_forward_param_sync = True
+            self.reducer.require_sync = True
+            self.reducer.prepare_for_backward()
+        else:
+            self.require_forward_param_sync = False
+            if torch.is_grad_enabled():
+                self.reducer.require_sync = False
                 self.reducer.armed = False
         return out
 

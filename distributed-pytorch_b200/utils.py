@@ -44,6 +44,28 @@ class MyTrainDataset(Dataset):
         return self.x[idx].to(device), self.y[idx].to(device)
 
 
+class DeviceShardLoader:
+    """A rank's ``DistributedSampler`` shard of a ``MyTrainDataset`` kept RESIDENT on the device and served
+    as batch views — the same rows, in the same order and with the same batch boundaries as
+    ``prepare_dataloader(dataset, batch_size)`` (ref:multigpu.py:72-79: ``shuffle=False`` on the loader,
+    ``DistributedSampler`` defaults, last batch kept), but with one H2D copy per epoch-set instead of one per
+    batch and no per-sample collation.  Iterating yields ``(source, targets)`` device tensors."""
+
+    def __init__(self, dataset: "MyTrainDataset", batch_size: int, device, sampler=None) -> None:
+        from torch.utils.data.distributed import DistributedSampler
+
+        self.sampler = sampler if sampler is not None else DistributedSampler(dataset)
+        self.batch_size = int(batch_size)
+        self.x, self.y = dataset.device_shard(list(self.sampler), device)
+
+    def __len__(self) -> int:
+        return (self.x.shape[0] + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for i in range(0, self.x.shape[0], self.batch_size):
+            yield self.x[i:i + self.batch_size], self.y[i:i + self.batch_size]
+
+
 class MyRandomDataset(Dataset):
     def __init__(self, size: int, input_shape: Sequence[int], target_shape: Sequence[int] = (1000,),
                  seed: Optional[int] = None):
