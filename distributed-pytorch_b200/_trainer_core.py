@@ -11,10 +11,27 @@ keep their barrier generation in device memory (no per-launch host state, see cs
 """
 from __future__ import annotations
 
-from typing import Callable, Optional
+from typing import Callable, Optional, Tuple
 
 import torch
-from torch.utils.data import DataLoader
+from torch.utils.data import DataLoader, Dataset
+from torch.utils.data.distributed import DistributedSampler
+
+
+def toy_train_objs() -> Tuple[Dataset, torch.nn.Module, torch.optim.Optimizer]:
+    """The objects every toy script trains (ref:multigpu.py:65-69, ref:multigpu_torchrun.py:71-75): 2048
+    ``MyTrainDataset`` rows, ``Linear(20, 1)``, SGD with lr 1e-3 built on the UN-wrapped model."""
+    from .utils import MyTrainDataset
+
+    net = torch.nn.Linear(MyTrainDataset.FEATURES, MyTrainDataset.TARGETS)
+    return MyTrainDataset(2048), net, torch.optim.SGD(net.parameters(), lr=1e-3)
+
+
+def sharded_loader(dataset: Dataset, batch_size: int) -> DataLoader:
+    """Per-rank loader (ref:multigpu.py:72-79): pinned memory, no loader-level shuffle, rows chosen by a
+    default ``DistributedSampler`` (which shuffles with seed 0 and is never re-seeded)."""
+    return DataLoader(dataset, batch_size=batch_size, sampler=DistributedSampler(dataset), shuffle=False,
+                      pin_memory=True)
 
 
 class TrainerCore:
@@ -32,6 +49,13 @@ class TrainerCore:
     _g_targets: Optional[torch.Tensor] = None
     _g_loss: Optional[torch.Tensor] = None
     graph_kernel_launches: int = 0  # b200ddp kernels captured per replayed step
+
+    def _adopt(self, wrapped: torch.nn.Module, train_data, optimizer: torch.optim.Optimizer, gpu_id: int,
+               save_every: int) -> None:
+        """Common constructor tail of the script Trainers."""
+        self.gpu_id, self.save_every = gpu_id, save_every
+        self.train_data, self.optimizer = train_data, optimizer
+        self.model = wrapped
 
     def _eager_step(self, source: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         self.optimizer.zero_grad()

@@ -31,99 +31,98 @@ from .utils import MyRandomDataset
 
 
 def load_train_objs():
+    """ResNet-50 (random init), 2048 synthetic 3x224x224 samples with 1000-way soft targets, SGD lr 1e-3
+    (ref:multigpu_profile.py:13-27; the commented-out vit_l_32 alternative is not carried over)."""
     from torchvision.models import resnet50
 
-    train_set = MyRandomDataset(2048, (3, 224, 224))
-    model = resnet50()
-    optimizer = torch.optim.SGD(model.parameters(), lr=1e-3)
-    return train_set, model, optimizer
+    net = resnet50()
+    return MyRandomDataset(2048, (3, 224, 224)), net, torch.optim.SGD(net.parameters(), lr=1e-3)
 
 
 class CudaProfilerWindow:
-    """start()/step()/stop() like torch.profiler.profile with schedule(wait, warmup, active): opens the CUDA
-    profiler range for the `active` steps only and wraps every step in an NVTX range."""
+    """start()/step()/stop() with torch.profiler's schedule semantics (wait, warmup, active): the CUDA
+    profiler range (cudaProfilerStart/Stop, honoured by ``ncu --profile-from-start off``) is open for the
+    ``active`` steps only, and every step sits inside its own NVTX range."""
 
     def __init__(self, wait: int = 1, warmup: int = 1, active: int = 5) -> None:
-        self.first = wait + warmup
-        self.last = wait + warmup + active
-        self.n = 0
-        self.open = False
-        self.in_range = False
+        self.first, self.last = wait + warmup, wait + warmup + active
+        self.n, self.open, self.in_range = 0, False, False
 
-    def _push(self) -> None:
-        torch.cuda.nvtx.range_push(f"b200ddp step {self.n}")
-        self.in_range = True
+    def _nvtx(self, push: bool) -> None:
+        if push:
+            torch.cuda.nvtx.range_push(f"b200ddp step {self.n}")
+        elif self.in_range:
+            torch.cuda.nvtx.range_pop()
+        self.in_range = push
+
+    def _window(self, open_it: bool) -> None:
+        torch.cuda.synchronize()
+        (torch.cuda.profiler.start if open_it else torch.cuda.profiler.stop)()
+        self.open = open_it
 
     def start(self) -> None:
         self.n = 0
-        self._push()
+        self._nvtx(True)
 
     def step(self) -> None:
-        if self.in_range:
-            torch.cuda.nvtx.range_pop()
-            self.in_range = False
+        self._nvtx(False)
         self.n += 1
         if self.n == self.first and not self.open:
-            torch.cuda.synchronize()
-            torch.cuda.profiler.start()
-            self.open = True
+            self._window(True)
         elif self.n == self.last and self.open:
-            torch.cuda.synchronize()
-            torch.cuda.profiler.stop()
-            self.open = False
-        self._push()
+            self._window(False)
+        self._nvtx(True)
 
     def stop(self) -> None:
-        if self.in_range:
-            torch.cuda.nvtx.range_pop()
-            self.in_range = False
+        self._nvtx(False)
         if self.open:
-            torch.cuda.synchronize()
-            torch.cuda.profiler.stop()
-            self.open = False
+            self._window(False)
 
 
 class Trainer:
+    """Same constructor and method names as ref:multigpu_profile.py:30-91."""
+
     def __init__(self, model, train_set, optimizer, device, batch_size, profile: bool = False) -> None:
+        self.device, self.batch_size = device, batch_size
+        self.train_set, self.optimizer = train_set, optimizer
         self.model = self.prepare_model_for_DDP(model, device)
-        self.train_set = train_set
-        self.optimizer = optimizer
-        self.device = device
-        self.batch_size = batch_size
         self.profiler = self._create_profiler() if profile else None
 
     def prepare_model_for_DDP(self, model, device):
-        model.to(device)
-        return DDP(model, [device])
+        return DDP(model.to(device), [device])
 
-    def run_batch(self, source, targets):
+    def run_batch(self, source, targets) -> None:
         self.optimizer.zero_grad()
-        source, targets = source.to(self.device), targets.to(self.device)
-        loss = F.cross_entropy(self.model(source), targets)
-        loss.backward()
+        logits = self.model(source.to(self.device))
+        F.cross_entropy(logits, targets.to(self.device)).backward()  # soft-label CE, ref:multigpu_profile.py:49
         self.optimizer.step()
 
-    def run_epoch(self, nb_epochs: int) -> None:
-        train_data = torch.utils.data.DataLoader(self.train_set, batch_size=32, shuffle=False,
-                                                 sampler=DistributedSampler(self.train_set))
-        if self.profiler:
-            self.profiler.start()
-        for epoch in range(nb_epochs):
-            print(f"[GPU{self.device}] Epoch {epoch} | No. of batches: {len(train_data)} | "
-                  f"Batchsize: {len(next(iter(train_data))[0])}")
-            for source, targets in train_data:
-                self.run_batch(source, targets)
-                if self.profiler:
-                    self.profiler.step()
-        if self.profiler:
-            self.profiler.stop()
+    def _loader(self):
+        # the reference hard-codes 32 here and ignores its batch_size argument (SURVEY §9 Q5); kept
+        return torch.utils.data.DataLoader(self.train_set, sampler=DistributedSampler(self.train_set), batch_size=32,
+                                           shuffle=False)
 
-    def save_checkpoint(self) -> None:
-        torch.save(self.model.state_dict(), "model_ddp.pth")  # wrapped state dict: module.-prefixed keys
-        print("Model state dict saved at model_ddp.pth")
+    def run_epoch(self, nb_epochs: int) -> None:
+        batches = self._loader()
+        prof = self.profiler
+        if prof:
+            prof.start()
+        for epoch in range(nb_epochs):
+            width = len(next(iter(batches))[0])
+            print(f"[GPU{self.device}] Epoch {epoch} | No. of batches: {len(batches)} | Batchsize: {width}")
+            for source, targets in batches:
+                self.run_batch(source, targets)
+                if prof:
+                    prof.step()
+        if prof:
+            prof.stop()
+
+    def save_checkpoint(self, path: str = "model_ddp.pth") -> None:
+        torch.save(self.model.state_dict(), path)  # the WRAPPED state dict: keys carry the module. prefix
+        print(f"Model state dict saved at {path}")
 
     def _create_profiler(self) -> CudaProfilerWindow:
-        return CudaProfilerWindow(wait=1, warmup=1, active=5)
+        return CudaProfilerWindow(wait=1, warmup=1, active=5)  # the reference's schedule, ref:multigpu_profile.py:82
 
 
 def ddp_setup(rank: int, world_size: int) -> None:
@@ -134,8 +133,8 @@ def ddp_setup(rank: int, world_size: int) -> None:
 
 def main(rank: int, world_size: int) -> None:
     ddp_setup(rank, world_size)
-    dataset, model, optimizer = load_train_objs()
-    trainer = Trainer(model, dataset, optimizer, device=rank, batch_size=32, profile=True)
+    train_set, net, sgd = load_train_objs()
+    trainer = Trainer(net, train_set, sgd, device=rank, batch_size=32, profile=True)
     trainer.run_epoch(3)
     if rank == 0:
         trainer.save_checkpoint()
@@ -143,5 +142,5 @@ def main(rank: int, world_size: int) -> None:
 
 
 if __name__ == "__main__":
-    n = torch.cuda.device_count()
-    mp.spawn(main, args=(n,), nprocs=n)
+    gpus = torch.cuda.device_count()
+    mp.spawn(main, nprocs=gpus, args=(gpus,))

@@ -85,3 +85,34 @@ def test_product_ddp_refuses_cpu_module():
 
     with pytest.raises(RuntimeError, match="no CPU path"):
         DDP(torch.nn.Linear(4, 2))
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under distributed-pytorch_b200/ (Python or C/CUDA) may import,
+    link or execute it, and the product has no CPU/NCCL implementation of the bucket engine."""
+    import glob
+
+    pkg = os.path.join(os.path.dirname(HEADER), "..", "distributed-pytorch_b200")
+    files = glob.glob(os.path.join(pkg, "*.py")) + glob.glob(os.path.join(pkg, "csrc", "*"))
+    assert files
+    for path in files:
+        text = open(path).read()
+        for needle in ("import oracle", "from oracle", "liboracle", "oracle/", "oracle."):
+            assert needle not in text, f"{os.path.basename(path)} references the oracle ({needle!r})"
+    reducer = open(os.path.join(pkg, "reducer.py")).read()
+    assert "dist.all_reduce" not in reducer and "all_reduce(" not in reducer  # no library collective on the path
+
+
+def test_profile_script_surface():
+    import inspect
+
+    from b200ddp import multigpu_profile as m
+
+    assert list(inspect.signature(m.Trainer.__init__).parameters) == ["self", "model", "train_set", "optimizer",
+                                                                      "device", "batch_size", "profile"]
+    for name in ("prepare_model_for_DDP", "run_batch", "run_epoch", "save_checkpoint", "_create_profiler"):
+        assert callable(getattr(m.Trainer, name))
+    assert list(inspect.signature(m.ddp_setup).parameters) == ["rank", "world_size"]
+    assert list(inspect.signature(m.main).parameters) == ["rank", "world_size"]
+    w = m.CudaProfilerWindow(wait=1, warmup=1, active=5)
+    assert (w.first, w.last) == (2, 7)
