@@ -32,6 +32,11 @@ def free_port() -> int:
 
 def _worker(rank: int, world: int, port: int, spec: Dict, ret) -> None:
     backend = spec["backend"]
+    # when the caller itself runs under torchrun, its TORCHELASTIC_USE_AGENT_STORE=True would make c10d look
+    # for the elastic agent's store at OUR port instead of starting a store daemon on rank 0: this world is
+    # independent of the launcher's, so the launcher's rendezvous variables are dropped
+    for var in ("TORCHELASTIC_USE_AGENT_STORE", "TORCHELASTIC_RESTART_COUNT", "TORCHELASTIC_RUN_ID"):
+        os.environ.pop(var, None)
     threads = spec.get("threads_per_rank")
     if threads:
         torch.set_num_threads(int(threads))
