@@ -117,31 +117,35 @@ class ClockSampler:
         import datetime
 
         marks = getattr(self, "marks", [])
-        total = 0
-        for line in out.splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
-                continue
-            total += 1
-            if len(marks) >= 2:
-                try:
-                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                except ValueError:
-                    ts = None
-                if ts is not None and not (marks[0] - 0.15 <= ts <= marks[-1] + 0.15):
+        rows = out.splitlines()
+        in_window = 0
+        for use_window in (True, False):  # if no sample fell inside the (possibly very short) timed window, use
+            if sm:                        # every sample of the run (taken under the same load) rather than none
+                break
+            for line in rows:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
                     continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+                if use_window and len(marks) >= 2:
+                    try:
+                        ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except ValueError:
+                        ts = None
+                    if ts is not None and not (marks[0] - 0.15 <= ts <= marks[-1] + 0.15):
+                        continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            in_window = len(sm) if use_window else in_window
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_timed_window": in_window}
 
 
 # ------------------------------------------------------------------------------------------------------
