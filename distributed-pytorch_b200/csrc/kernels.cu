@@ -291,17 +291,25 @@ constexpr uint32_t kCopyTile = kCopyThreads * kCopyUnroll;  // vectors per tile 
 // One launch moves bucket vectors [vec_begin, vec_end) (all inside the tensors of `tt`).
 // HBM-bound: reads S + writes S bytes for S bytes of gradients.
 template <int DT, bool UNFLATTEN>
-__global__ void __launch_bounds__(kCopyThreads)
+__global__ void __launch_bounds__(kCopyThreads, 4)  // <= 32 registers: 4 CTAs = 2048 threads per SM
 multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* __restrict__ bucket,
                          uint32_t vec_begin, uint32_t vec_end, float scale) {
   __shared__ SmemTable s;
   load_table(s, tt);
   const int n = tt.n;
-  const uint32_t ntiles = (vec_end - vec_begin + kCopyTile - 1) / kCopyTile;
+  // Even split: every CTA owns the same number of vectors (+-one 8 KiB granule) of the launch's range.  The
+  // grid is sized to be fully co-resident (launch_flatten), so it runs as ONE wave and all CTAs finish
+  // together — a tile-strided loop left some CTAs with one 32 KiB tile more than others (2048 tiles over
+  // 592 CTAs: a 15 % tail at 64 MiB).
+  const uint32_t granules = (vec_end - vec_begin + kCopyThreads - 1) / kCopyThreads;
+  const uint32_t per = granules / gridDim.x, extra = granules % gridDim.x;
+  const uint32_t g0 = blockIdx.x * per + min(blockIdx.x, extra);
+  const uint32_t g1 = g0 + per + (blockIdx.x < extra ? 1u : 0u);
+  const uint32_t r0 = vec_begin + g0 * kCopyThreads;
+  const uint32_t r1 = min(vec_end, vec_begin + g1 * kCopyThreads);
   uint4* bvec = reinterpret_cast<uint4*>(bucket);
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t v0 = vec_begin + tile * kCopyTile;
-    const uint32_t v1 = min(v0 + kCopyTile, vec_end);
+  for (uint32_t v0 = r0; v0 < r1; v0 += kCopyTile) {
+    const uint32_t v1 = min(v0 + kCopyTile, r1);
     const int t_lo = locate(s.off, 0, n - 1, v0);
     const int t_hi = locate(s.off, t_lo, n - 1, v1 - 1);
     const uint64_t first = static_cast<uint64_t>(v0 - s.off[t_lo]);
@@ -854,8 +862,9 @@ inline int clamp_grid(uint64_t want, int max_ctas, int dflt) {
 cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_begin, uint32_t vec_end, int dtype,
                            float scale, bool unflatten, cudaStream_t s) {
   if (vec_end <= vec_begin || tt.n <= 0) return cudaSuccess;
-  const uint32_t ntiles = (vec_end - vec_begin + kCopyTile - 1) / kCopyTile;
-  const int grid = static_cast<int>(ntiles < uint32_t(kNumSMs * 4) ? ntiles : uint32_t(kNumSMs * 4));
+  // one co-resident wave: 4 CTAs of 512 threads per SM (__launch_bounds__(512, 4), 32 registers, no spills)
+  const uint32_t granules = (vec_end - vec_begin + kCopyThreads - 1) / kCopyThreads;
+  const int grid = static_cast<int>(granules < uint32_t(kNumSMs * 4) ? granules : uint32_t(kNumSMs * 4));
   unsigned char* b = static_cast<unsigned char*>(bucket);
   B200_DISPATCH_DT(dtype, {
     if (unflatten)
