@@ -293,22 +293,23 @@ constexpr uint32_t kCopyTile = kCopyThreads * kCopyUnroll;  // vectors per tile 
 template <int DT, bool UNFLATTEN>
 __global__ void __launch_bounds__(kCopyThreads, 4)  // <= 32 registers: 4 CTAs = 2048 threads per SM
 multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* __restrict__ bucket,
-                         uint32_t vec_begin, uint32_t vec_end, float scale) {
+                         uint32_t vec_begin, uint32_t vec_end, float scale, int even_split) {
   __shared__ SmemTable s;
   load_table(s, tt);
   const int n = tt.n;
-  // Even split: every CTA owns the same number of vectors (+-one 8 KiB granule) of the launch's range.  The
-  // grid is sized to be fully co-resident (launch_flatten), so it runs as ONE wave and all CTAs finish
-  // together — a tile-strided loop left some CTAs with one 32 KiB tile more than others (2048 tiles over
-  // 592 CTAs: a 15 % tail at 64 MiB).
+  // The grid is one co-resident wave (launch_flatten).  Default: 32 KiB tiles dealt round-robin (the CTAs
+  // sweep memory as a sliding window).  even_split: every CTA owns one contiguous, equal share instead —
+  // no tail, but measurably worse DRAM locality (see launch_flatten).
   const uint32_t granules = (vec_end - vec_begin + kCopyThreads - 1) / kCopyThreads;
   const uint32_t per = granules / gridDim.x, extra = granules % gridDim.x;
   const uint32_t g0 = blockIdx.x * per + min(blockIdx.x, extra);
   const uint32_t g1 = g0 + per + (blockIdx.x < extra ? 1u : 0u);
-  const uint32_t r0 = vec_begin + g0 * kCopyThreads;
-  const uint32_t r1 = min(vec_end, vec_begin + g1 * kCopyThreads);
+  // even_split == 0: tiles are dealt round-robin instead (CTAs sweep memory as a sliding window)
+  const uint32_t r0 = even_split ? vec_begin + g0 * kCopyThreads : vec_begin + blockIdx.x * kCopyTile;
+  const uint32_t r1 = even_split ? min(vec_end, vec_begin + g1 * kCopyThreads) : vec_end;
+  const uint32_t stride = even_split ? kCopyTile : gridDim.x * kCopyTile;
   uint4* bvec = reinterpret_cast<uint4*>(bucket);
-  for (uint32_t v0 = r0; v0 < r1; v0 += kCopyTile) {
+  for (uint32_t v0 = r0; v0 < r1; v0 += stride) {
     const uint32_t v1 = min(v0 + kCopyTile, r1);
     const int t_lo = locate(s.off, 0, n - 1, v0);
     const int t_hi = locate(s.off, t_lo, n - 1, v1 - 1);
@@ -866,11 +867,16 @@ cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_beg
   const uint32_t granules = (vec_end - vec_begin + kCopyThreads - 1) / kCopyThreads;
   const int grid = static_cast<int>(granules < uint32_t(kNumSMs * 4) ? granules : uint32_t(kNumSMs * 4));
   unsigned char* b = static_cast<unsigned char*>(bucket);
+  // Work split, A/B-measured on one box (tools/ab_copy.py): dealing 32 KiB tiles round-robin makes the
+  // co-resident CTAs sweep memory as a sliding window and beat an even per-CTA split by 2-7 % at 16-256 MiB
+  // (25 MiB: 4.88 vs 4.58 TB/s), so it is the default; B200DDP_COPY_SPLIT=even selects the other.
+  const char* mode = getenv("B200DDP_COPY_SPLIT");
+  const int even = (mode && mode[0] == 'e') ? 1 : 0;
   B200_DISPATCH_DT(dtype, {
     if (unflatten)
-      multi_tensor_copy_kernel<DT, true><<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale);
+      multi_tensor_copy_kernel<DT, true><<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even);
     else
-      multi_tensor_copy_kernel<DT, false><<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale);
+      multi_tensor_copy_kernel<DT, false><<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even);
   });
   return cudaGetLastError();
 }
