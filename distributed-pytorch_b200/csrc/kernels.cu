@@ -684,13 +684,16 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
 constexpr int kLLThreads = 256;
 constexpr uint32_t kLLWordsPerCta = 1024;
 
+// One 64-bit scalar access per (data, tag) pair: single-copy atomic by the PTX memory model (an aligned
+// scalar access is never torn), so a reader that sees the tag also sees the data it travelled with.
 __device__ __forceinline__ void st_ll(uint2* p, uint32_t data, uint32_t tag) {
-  asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
+  const uint64_t packed = static_cast<uint64_t>(data) | (static_cast<uint64_t>(tag) << 32);
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(packed) : "memory");
 }
 __device__ __forceinline__ uint2 ld_ll(const uint2* p) {
-  uint2 r;
-  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
-  return r;
+  uint64_t packed;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(packed) : "l"(p) : "memory");
+  return make_uint2(static_cast<uint32_t>(packed), static_cast<uint32_t>(packed >> 32));
 }
 
 // bucket word w (4 bytes) of tensor t, read from the tensor's storage and pre-scaled

@@ -177,3 +177,76 @@ def test_script_surface_matches_reference_signatures():
     assert a.shape == (3, 8, 8) and b.shape == (1000,)
     loader = multigpu.prepare_dataloader(utils.MyTrainDataset(64, seed=1), 32) if torch.distributed.is_initialized() else None
     assert loader is None or loader.batch_size == 32
+
+
+def test_mixed_dtypes_frozen_parameters_and_env_cap(monkeypatch):
+    """Buckets never mix dtypes (BucketKey = dtype+device), frozen parameters are ignored, and
+    B200DDP_BUCKET_MB overrides the default cap like bucket_cap_mb does."""
+    class Mixed(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Linear(16, 16)
+            self.b = nn.Linear(16, 16).to(torch.bfloat16)
+            self.c = nn.Linear(16, 4)
+            self.frozen = nn.Linear(4, 4)
+            for p in self.frozen.parameters():
+                p.requires_grad_(False)
+
+        def forward(self, x):
+            return self.frozen(self.c(self.b(self.a(x).to(torch.bfloat16)).float()))
+
+    eng = RecordingEngine()
+    ddp = DDP(Mixed(), _engine=eng)
+    params = ddp.reducer.params
+    assert len(params) == 6  # the frozen layer's two tensors are not reduced
+    for spec in eng.plans[0]:
+        dts = {params[i].dtype for i in spec.param_indices}
+        assert len(dts) == 1
+        assert spec.elem_size == params[spec.param_indices[0]].element_size()
+    assert {spec.dtype_code for spec in eng.plans[0]} == {0, 1}
+    ddp(torch.randn(3, 16)).sum().backward()
+    assert sorted(eng.launched) == list(range(len(eng.plans[0])))
+    assert all(p.grad is None for p in ddp.module.frozen.parameters())
+
+    monkeypatch.setenv("B200DDP_BUCKET_MB", "0.001")
+    small = DDP(_mlp(), _engine=RecordingEngine())
+    assert small.bucket_bytes_cap == int(0.001 * 1024 * 1024)
+    from oracle import bucket_oracle as bo
+
+    sizes = [p.numel() * 4 for p in small.reducer.params]
+    cap = small.bucket_bytes_cap
+    want = bo.ddp_initial_buckets(sizes, ["k"] * len(sizes), first_cap=cap, cap=cap)
+    assert [b.param_indices for b in small.reducer.buckets] == want and len(want) == 4
+
+
+def test_buffer_sync_flag_follows_the_previous_forward():
+    """require_forward_param_sync mirrors torch (distributed.py:1637-1650): buffers are broadcast before a
+    forward iff the previous forward was a gradient-synchronising one."""
+    class Counting(RecordingEngine):
+        def __init__(self):
+            super().__init__(world_size=2)
+            self.bcasts = 0
+
+        def broadcast_tensors(self, tensors, root=0):
+            self.bcasts += 1
+
+    eng = Counting()
+    model = nn.Sequential(nn.Linear(4, 4), nn.BatchNorm1d(4))
+    ddp = DDP(model, _engine=eng)
+    assert eng.bcasts == 1  # construction-time parameter + buffer sync
+    x = torch.randn(8, 4)
+    ddp(x).sum().backward()
+    assert eng.bcasts == 2  # first forward syncs buffers
+    with ddp.no_sync():
+        ddp(x).sum().backward()
+    assert eng.bcasts == 3  # previous forward was synchronising
+    ddp(x).sum().backward()
+    assert eng.bcasts == 3  # previous forward was inside no_sync(): no buffer sync now
+    with torch.no_grad():
+        ddp(x)
+    assert eng.bcasts == 4
+    ddp(x).sum().backward()
+    assert eng.bcasts == 4  # previous forward ran without grad
+    plain = DDP(nn.Sequential(nn.Linear(4, 4), nn.BatchNorm1d(4)), broadcast_buffers=False, _engine=Counting())
+    plain(x).sum().backward()
+    assert plain.engine.bcasts == 1
