@@ -56,8 +56,6 @@ class DistributedDataParallel(nn.Module):
         if find_unused_parameters:
             raise NotImplementedError("find_unused_parameters=True is outside the reference's path "
                                       "(DDP(model, device_ids=[gpu_id])) and is not supported")
-        if gradient_as_bucket_view:
-            raise NotImplementedError("gradient_as_bucket_view is not implemented yet (SURVEY §8 f.1)")
         if process_group is not None:
             raise NotImplementedError("b200ddp spans the default process group (one 8-GPU NVSwitch box)")
         if device_ids is not None and len(device_ids) > 1:
@@ -96,6 +94,12 @@ class DistributedDataParallel(nn.Module):
                                                   staging_bytes=staging)
         else:
             self.engine = _engine
+        if gradient_as_bucket_view:
+            # .grad of every parameter in a large bucket becomes a view of the reduced bucket in
+            # the arena (no unflatten pass); as in torch, such gradients must not be detach_()-ed, and the
+            # one-time bucket rebuild is skipped so that live views never change meaning
+            self.engine.grad_views = True
+        self.gradient_as_bucket_view = bool(gradient_as_bucket_view)
         self._verify_param_shapes(params)
         # ranks start from different random initialisations (ref:multigpu.py:67); rank 0 wins
         # (torch:nn/parallel/distributed.py:883-890)

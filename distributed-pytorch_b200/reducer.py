@@ -46,9 +46,11 @@ class BucketEngine:
         """Called whenever the bucket list changes (construction, rebuild)."""
         raise NotImplementedError
 
-    def reduce_bucket(self, bucket: BucketSpec, grads: List[torch.Tensor]) -> None:
+    def reduce_bucket(self, bucket: BucketSpec, grads: List[torch.Tensor]) -> Optional[List[torch.Tensor]]:
         """Average ``grads`` (this bucket's gradients, in bucket order) over all ranks, in place.
-        Must only enqueue work ordered after the caller's current stream; must not block the host."""
+        Must only enqueue work ordered after the caller's current stream; must not block the host.
+        May return replacement gradient tensors (views of the reduced bucket, gradient_as_bucket_view)
+        which the Reducer then installs as ``param.grad``; ``None`` means the given tensors were updated."""
         raise NotImplementedError
 
     def finalize(self) -> None:
@@ -97,6 +99,10 @@ class P2PEngine(BucketEngine):
         self._max_table = P2PComm.max_table_tensors()
         self._keepalive: List[torch.Tensor] = []
         self._bcast_plans: Dict[tuple, tuple] = {}
+        #: gradient_as_bucket_view (reducer.hpp:238,328-334): after the allreduce the parameters' ``.grad``
+        #: become views of the reduced bucket in the arena instead of being copied back (no unflatten pass)
+        self.grad_views = False
+        self._view_cache: Dict[int, List[torch.Tensor]] = {}
 
     # ---- planning -----------------------------------------------------------------------------------
     def plan(self, buckets: List[BucketSpec]) -> None:
@@ -115,6 +121,7 @@ class P2PEngine(BucketEngine):
             raise RuntimeError(f"bucket layout needs {layout.total_bytes} bytes but the arena has "
                                f"{self.comm.arena_bytes}")
         self._tables.clear()
+        self._view_cache.clear()
         if multi:
             self.comm.stream_wait(self._stream_ptr, torch.cuda.current_stream(self.device).cuda_stream)
             for b in buckets:  # the fused path's tagged slots must start from zero
@@ -135,7 +142,16 @@ class P2PEngine(BucketEngine):
         return table
 
     # ---- hot path -----------------------------------------------------------------------------------
-    def reduce_bucket(self, bucket: BucketSpec, grads: List[torch.Tensor]) -> None:
+    def _bucket_views(self, bucket: BucketSpec, like: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        views = self._view_cache.get(bucket.index)
+        if views is None:
+            es = bucket.elem_size
+            views = [self.comm.view(bucket.out_off + off * es, n * es, g.dtype).view(g.shape)
+                     for off, n, g in zip(bucket.offsets_el, bucket.lengths_el, like)]
+            self._view_cache[bucket.index] = views
+        return views
+
+    def reduce_bucket(self, bucket: BucketSpec, grads: List[torch.Tensor]) -> Optional[List[torch.Tensor]]:
         comm, s = self.comm, self._stream_ptr
         work = grads
         if not all(g.is_contiguous() for g in grads):
@@ -143,6 +159,16 @@ class P2PEngine(BucketEngine):
             work = [g if g.is_contiguous() else g.contiguous() for g in grads]
         comm.stream_wait(s, torch.cuda.current_stream(self.device).cuda_stream)
         table = self._table(bucket, work)
+        if self.grad_views and not bucket.fused:
+            # flatten(+scale) into the arena (an in-place scale when .grad already is the view), reduce in
+            # place, and hand the arena views back instead of copying out.  Small (fused) buckets keep their
+            # own storage: their single launch already writes the result straight into the gradients.
+            comm.flatten_scale(table, bucket.dtype_code, bucket.arena_off, self.scale, s)
+            if self.world_size > 1:
+                comm.allreduce(bucket.arena_off, bucket.out_off, bucket.nbytes, bucket.dtype_code, bucket.algo,
+                               self.max_ctas, s)
+            self._keepalive.extend(work)  # the flatten kernel on the side stream still reads them
+            return self._bucket_views(bucket, grads)
         if bucket.fused:
             comm.fused_bucket(table, bucket.dtype_code, bucket.arena_off, bucket.nbytes, self.scale, s)
         else:
@@ -157,6 +183,7 @@ class P2PEngine(BucketEngine):
                     if w is not g:
                         g.copy_(w)
             self._keepalive.extend(work)
+        return None
 
     def finalize(self) -> None:
         self.comm.stream_wait(torch.cuda.current_stream(self.device).cuda_stream, self._stream_ptr)
@@ -353,7 +380,10 @@ class Reducer:
             n = len(self.buckets)
             while self._next_bucket < n and self._bucket_ready[self._next_bucket]:
                 b = self.buckets[self._next_bucket]
-                self.engine.reduce_bucket(b, [self.params[i].grad for i in b.param_indices])
+                new = self.engine.reduce_bucket(b, [self.params[i].grad for i in b.param_indices])
+                if new is not None:  # gradient_as_bucket_view: .grad becomes a view of the reduced bucket
+                    for i, g in zip(b.param_indices, new):
+                        self.params[i].grad = g
                 self._next_bucket += 1
 
     def _finalize_backward(self) -> None:
@@ -370,7 +400,13 @@ class Reducer:
         self._unfinished = False
         self.iterations += 1
         if not self.has_rebuilt:
-            self._rebuild_buckets()
+            if getattr(self.engine, "grad_views", False):
+                # with gradient_as_bucket_view the live .grad tensors are views of the CURRENT layout (the
+                # optimizer reads them right after this callback): the layout is never changed under them
+                self.has_rebuilt = True
+                self._ready_order = []
+            else:
+                self._rebuild_buckets()
 
     def _rebuild_buckets(self) -> None:
         """One-time re-bucketing in gradient-ready order (rank 0's order wins on every rank)."""

@@ -74,7 +74,7 @@ def raw_allreduce(rank, world, mem="vmm"):
     return res
 
 
-def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None):
+def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None, views=False):
     """Our DDP and stock torch-DDP/NCCL side by side: same seeded weights, same per-rank batches."""
     import copy
 
@@ -86,8 +86,8 @@ def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None):
     base = wl.build().to(dev)
     ours_m, ref_m = copy.deepcopy(base), copy.deepcopy(base)
     kw = {} if bucket_cap_mb is None else {"bucket_cap_mb": bucket_cap_mb}
-    ours = DDP(ours_m, device_ids=[rank], **kw)
-    ref = torch.nn.parallel.DistributedDataParallel(ref_m, device_ids=[rank], **kw)
+    ours = DDP(ours_m, device_ids=[rank], gradient_as_bucket_view=bool(views), **kw)
+    ref = torch.nn.parallel.DistributedDataParallel(ref_m, device_ids=[rank], gradient_as_bucket_view=bool(views), **kw)
     o1 = torch.optim.SGD(ours_m.parameters(), lr=1e-3)
     o2 = torch.optim.SGD(ref_m.parameters(), lr=1e-3)
     gen = torch.Generator().manual_seed(99 + rank)

@@ -123,6 +123,44 @@ def test_cuda_graph_step_matches_eager_training(pg1):
         multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
 
 
+def test_gradient_as_bucket_view_world1(pg1):
+    """gradient_as_bucket_view=True: gradients of large buckets are views of the arena (no unflatten pass), the
+    values and the training trajectory are those of the plain model; both zero_grad modes."""
+    from b200ddp import DDP, workloads
+
+    wl = workloads.get("mlp")
+    torch.manual_seed(2)
+    model = torch.nn.Sequential(torch.nn.Linear(20, 600), torch.nn.ReLU(), torch.nn.Linear(600, 600), torch.nn.ReLU(),
+                                torch.nn.Linear(600, 7)).cuda()
+    plain = copy.deepcopy(model)
+    ddp = DDP(model, device_ids=[0], bucket_cap_mb=1.0, gradient_as_bucket_view=True)
+    comm = ddp.engine.comm
+    lo, hi = comm.arena_ptr, comm.arena_ptr + comm.arena_bytes
+    o1 = torch.optim.SGD(model.parameters(), lr=1e-2)
+    o2 = torch.optim.SGD(plain.parameters(), lr=1e-2)
+    gen = torch.Generator().manual_seed(8)
+    for step in range(5):
+        x, y = wl.batch(16, torch.device("cuda"), gen)
+        set_none = step < 3
+        o1.zero_grad(set_to_none=set_none)
+        o2.zero_grad(set_to_none=set_none)
+        wl.loss(ddp(x), y).backward()
+        wl.loss(plain(x), y).backward()
+        torch.cuda.synchronize()
+        n_views = 0
+        for p, q in zip(model.parameters(), plain.parameters()):
+            assert torch.equal(p.grad, q.grad), f"step {step}"
+            n_views += lo <= p.grad.data_ptr() < hi
+        assert n_views >= 2, "the 600x600 layer's bucket must be served as arena views"
+        o1.step()
+        o2.step()
+    torch.cuda.synchronize()
+    for p, q in zip(model.parameters(), plain.parameters()):
+        assert torch.equal(p, q)
+    assert not any(b.fused for b in ddp.reducer.buckets if b.nbytes > (256 << 10))
+    ddp.shutdown()
+
+
 def test_product_path_requires_cuda_module(pg1):
     from b200ddp import DDP
 
@@ -304,4 +342,14 @@ def test_multigpu_ddp_matches_stock_nccl_ddp(workload):
     tol = 2e-2 if workload.endswith("bf16") else 1e-6
     for r in range(world):
         assert out[r]["worst_rel"] <= tol, out[r]
+        assert out[r]["weights_equal_across_ranks"]
+
+
+@needs_multi
+@pytest.mark.timeout(900)
+def test_multigpu_gradient_as_bucket_view_matches_stock_nccl_ddp():
+    world = min(torch.cuda.device_count(), 8)
+    out = _spawn_mp("ddp_vs_nccl", world, workload="slices", views=True)
+    for r in range(world):
+        assert out[r]["worst_rel"] <= 1e-6, out[r]
         assert out[r]["weights_equal_across_ranks"]
