@@ -204,6 +204,14 @@ class P2PComm:
     def mem_mode(self) -> str:
         return {_lib.MEM_IPC: "ipc", _lib.MEM_VMM: "vmm"}.get(self._lib.b200ddp_mem_mode(self._ctx), "?")
 
+    @property
+    def ctx_address(self) -> int:
+        return int(self._ctx.value)
+
+    def function_table(self) -> dict:
+        """name -> address of every C-ABI entry point (for the native hook loop, which calls the same ABI)."""
+        return {name: C.cast(getattr(self._lib, name), C.c_void_p).value for name, _, _ in _lib.SYMBOLS}
+
     def pick_algo(self, nbytes: int) -> int:
         return int(self._lib.b200ddp_pick_algo(self._ctx, nbytes))
 

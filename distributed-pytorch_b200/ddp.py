@@ -157,7 +157,7 @@ class DistributedDataParallel(nn.Module):
             self.require_forward_param_sync = False
             if torch.is_grad_enabled():
                 self.reducer.require_sync = False
-                self.reducer.armed = False
+                self.reducer.disarm()
         return out
 
     @contextmanager

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 from torch.autograd import Variable
 
-from . import _lib
+from . import _lib, _native
 from .bucketing import (
     DEFAULT_BUCKET_BYTES_CAP,
     DEFAULT_FIRST_BUCKET_BYTES,
@@ -313,7 +313,16 @@ class Reducer:
         self._ready_order: List[int] = []
         self._unfinished = False
         self.iterations = 0
-        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+        # opt-in (B200DDP_NATIVE=1): the same state machine in C++ on the autograd thread (csrc/native_reducer.cpp)
+        self._native = None
+        self._hooks = []
+        if _native.wanted() and isinstance(engine, P2PEngine) and not engine.grad_views:
+            mod = _native.build_native()
+            self._native = mod.NativeReducer(engine.comm.ctx_address, engine.comm.function_table(), engine.world_size,
+                                             engine._stream_ptr, engine.max_ctas, self.params)
+            self._native.configure(self._native_buckets())
+        else:
+            self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
 
     # ---- bucket bookkeeping -------------------------------------------------------------------------
     def _install(self, bucket_indices: List[List[int]]) -> None:
@@ -328,10 +337,22 @@ class Reducer:
         for b in specs:
             for i in b.param_indices:
                 self._param_bucket[i] = b.index
+        if getattr(self, "_native", None) is not None:
+            self._native.configure(self._native_buckets())
         self._pending = [0] * len(specs)
         self._bucket_ready = [False] * len(specs)
         self._param_seen = [False] * len(self.params)
         self._next_bucket = 0
+
+    def _native_buckets(self):
+        return [(b.param_indices, b.offsets_el, b.lengths_el, b.dtype_code, b.nbytes, b.arena_off, b.out_off, b.algo,
+                 b.fused) for b in self.buckets]
+
+    def disarm(self) -> None:
+        """The coming backward must not reduce (no_sync, or a forward without grad)."""
+        self.armed = False
+        if self._native is not None:
+            self._native.disarm()
 
     def bucket_sizes(self) -> List[int]:
         return [b.payload_bytes for b in self.buckets]
@@ -340,6 +361,17 @@ class Reducer:
     def prepare_for_backward(self) -> None:
         """Arm the reducer for the backward of the forward that just ran
         (Reducer::prepare_for_backward, called from DDP._post_forward, distributed.py:1648)."""
+        if self._native is not None:
+            if not self.has_rebuilt and self._native.iterations() >= 1:
+                # the one-time rebuild, driven from here like torch drives it from the next forward
+                self._ready_order = list(self._native.take_ready_order())
+                self._rebuild_buckets()
+            self.iterations = int(self._native.iterations())
+            if self.require_sync:
+                self._native.prepare()
+            else:
+                self._native.disarm()
+            return
         if self._unfinished:
             raise RuntimeError(
                 "Expected to have finished reduction in the prior iteration before starting a new one. "
@@ -425,6 +457,9 @@ class Reducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        if self._native is not None:
+            self._native.remove_hooks()
+            self._native = None
 
 
 def arena_bytes_for(params: Sequence[torch.nn.Parameter]) -> int:

@@ -64,8 +64,11 @@ def test_trainer_world1_matches_plain_training_bitwise(pg1):
         multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
 
 
-def test_world1_multibucket_three_kernel_path_bitwise(pg1):
+@pytest.mark.parametrize("native", [False, True], ids=["python-hooks", "native-hooks"])
+def test_world1_multibucket_three_kernel_path_bitwise(pg1, native, monkeypatch):
     from b200ddp import DDP, workloads
+
+    monkeypatch.setenv("B200DDP_NATIVE", "1" if native else "0")
 
     wl = workloads.get("mlp")
     torch.manual_seed(1)
@@ -86,6 +89,10 @@ def test_world1_multibucket_three_kernel_path_bitwise(pg1):
     sizes = ddp.reducer.bucket_sizes()
     assert len(sizes) >= 2 and any(not b.fused for b in ddp.reducer.buckets)
     assert ddp.reducer.has_rebuilt
+    assert (ddp.reducer._native is not None) == native
+    if native:  # the C++ loop launched every bucket of every iteration through the C ABI, in index order
+        assert ddp.reducer._native.iterations() == 3
+        assert ddp.reducer._native.launched_buckets()[-len(sizes):] == list(range(len(sizes)))
     ddp.shutdown()
 
 
@@ -168,7 +175,8 @@ def test_product_path_requires_cuda_module(pg1):
         DDP(torch.nn.Linear(4, 2))
 
 
-def test_loopback_ws2_replays_reference_trainer():
+@pytest.mark.parametrize("native", [False, True], ids=["python-hooks", "native-hooks"])
+def test_loopback_ws2_replays_reference_trainer(native, monkeypatch):
     """Two ranks on one GPU, each with its own stream, model replica, Reducer and arena context; inputs,
     initial weights and expected gradients are the golden vectors of the REFERENCE's Trainer (ws=2)."""
     from b200ddp import DDP
@@ -177,6 +185,7 @@ def test_loopback_ws2_replays_reference_trainer():
     from oracle import allreduce_oracle as ao
     from tests.helpers import rel_err
 
+    monkeypatch.setenv("B200DDP_NATIVE", "1" if native else "0")
     fx = torch.load(os.path.join(GOLD, "ref_trainer_ws2.pt"))["cases"]["mse"]
     dev = torch.device("cuda", 0)
     # stage every batch on the GPU first: in a loop-back world ONE host thread drives both ranks, so it must
