@@ -111,3 +111,46 @@ def test_ws2_batchnorm_buffers_and_no_sync_match_stock_ddp():
     for r in range(2):
         assert out[r]["worst"] <= 1e-6, out[r]
         assert out[r]["buffers_equal"]
+
+
+@settings(max_examples=200, deadline=None)
+@given(
+    numels=st.lists(st.integers(min_value=0, max_value=100_000), min_size=1, max_size=30),
+    esize=st.sampled_from([2, 4]),
+    start=st.integers(min_value=0, max_value=1 << 20),
+    modes=st.lists(st.sampled_from(["plain", "oop", "region"]), min_size=1, max_size=6),
+)
+def test_arena_layout_invariants(numels, esize, start, modes):
+    """Every tensor starts on a 16-byte boundary inside its bucket without overlapping its neighbour; bucket
+    regions are 4 KiB aligned, never overlap and never precede the staging region."""
+    from b200ddp.bucketing import BucketLayout, layout_bucket
+
+    spec = layout_bucket(0, list(range(len(numels))), numels, dtype_code=0 if esize == 4 else 1, elem_size=esize)
+    epv = 16 // esize
+    end = 0
+    for off, n in zip(spec.offsets_el, spec.lengths_el):
+        assert off % epv == 0 and off >= end
+        end = off + n
+    assert spec.nbytes % 16 == 0 and spec.nbytes >= max(16, end * esize) and spec.nbytes < end * esize + 16 * len(numels) + 16
+    lay = BucketLayout(start=start)
+    assert lay.total_bytes >= start and lay.total_bytes % 4096 == 0
+    spans = []
+    for k, mode in enumerate(modes):
+        b = layout_bucket(k, [0], [numels[0] + k], dtype_code=0, elem_size=4)
+        before = lay.total_bytes
+        if mode == "region":
+            region = 4 * 8 * b.nbytes
+            lay.place(b, region_bytes=region)
+            need = region
+        else:
+            lay.place(b, out_of_place=(mode == "oop"))
+            need = b.nbytes * (2 if mode == "oop" else 1)
+        assert b.arena_off == before and b.arena_off % 4096 == 0
+        assert lay.total_bytes - before >= need and lay.total_bytes % 4096 == 0
+        if mode == "oop":
+            assert b.out_off >= b.arena_off + b.nbytes and b.out_off % 4096 == 0
+        else:
+            assert b.out_off == b.arena_off
+        spans.append((before, lay.total_bytes))
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
