@@ -123,13 +123,16 @@ class P2PEngine(BucketEngine):
         self._tables.clear()
         self._view_cache.clear()
         if multi:
+            # (Re-)laying out the arena is collective and fenced on both sides.  Barrier 1: every rank has
+            # finished every kernel of the OLD layout (the fused kernels have no trailing barrier, so a slow
+            # peer may still be reading this rank's staging slot when this rank's kernel has already ended) —
+            # only then may the bytes be reused.  Then the fused path's tagged slots are zeroed.  Barrier 2:
+            # every rank's slots are cleared before any peer pushes into them.
             self.comm.stream_wait(self._stream_ptr, torch.cuda.current_stream(self.device).cuda_stream)
-            for b in buckets:  # the fused path's tagged slots must start from zero
+            self.comm.barrier(self._stream_ptr)
+            for b in buckets:
                 if b.fused:
                     self.comm.clear(b.arena_off, self.comm.fused_region_bytes(b.nbytes), self._stream_ptr)
-            # (re-)laying out the arena is collective: fence it so that no rank touches a new region while a
-            # peer's earlier kernel (old layout) may still read the same bytes, and so that every rank's
-            # slots are cleared before any peer pushes into them
             self.comm.barrier(self._stream_ptr)
 
     def _table(self, bucket: BucketSpec, tensors: Sequence[torch.Tensor]) -> TensorTable:
