@@ -171,7 +171,9 @@ struct b200ddp_ctx {
   uint32_t* err_host = nullptr;
   uint32_t* err_dev = nullptr;
   cudaEvent_t ev = nullptr;
-  uint32_t timeout_ms = 20000;
+  // like a collective watchdog, not a latency bound: a peer may legitimately be late by minutes (rank 0 writing
+  // a checkpoint while the others already wait in the next step's first bucket)
+  uint32_t timeout_ms = 600000;
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::string err;

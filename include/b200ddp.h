@@ -166,7 +166,8 @@ int b200ddp_stream_wait(b200ddp_ctx* ctx, void* waiter, void* signaled);
 /* Returns 0, or B200DDP_ETIMEOUT if any kernel since the last poll observed a peer timeout (the flag
  * lives in mapped host memory; polling does not synchronise the device). */
 int b200ddp_poll_error(b200ddp_ctx* ctx);
-/* In-kernel barrier timeout in milliseconds (default 20000). */
+/* In-kernel barrier timeout in milliseconds (default 600000 = 10 minutes, the order of NCCL's watchdog: a peer
+ * may legitimately arrive late, e.g. while rank 0 writes a checkpoint). */
 int b200ddp_set_timeout_ms(b200ddp_ctx* ctx, uint32_t ms);
 /* Number of kernels this context has launched since init. */
 uint64_t b200ddp_launch_count(b200ddp_ctx* ctx);
