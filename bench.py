@@ -219,6 +219,7 @@ def main_b200(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit(f"--gpus {args.gpus} must be launched with torch.distributed.run --nproc-per-node {args.gpus}")
+    os.environ.setdefault("B200DDP_TIMEOUT_MS", "60000")  # a benchmark run should fail fast if a rank dies
     os.environ.setdefault("RANK", "0")
     os.environ.setdefault("LOCAL_RANK", "0")
     os.environ.setdefault("WORLD_SIZE", "1")

@@ -122,6 +122,7 @@ def entry(rank, world, port, fn_name, kw, ret):
     from b200ddp import destroy_process_group, init_process_group
 
     os.environ["LOCAL_RANK"] = str(rank)
+    os.environ.setdefault("B200DDP_TIMEOUT_MS", "30000")
     torch.cuda.set_device(rank)
     init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
