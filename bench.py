@@ -429,7 +429,7 @@ def main_b200(args):
                          f"{r['threads_per_rank']} threads, via oracle/ref_ddp.py"}
 
     line = {
-        "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
+        "impl": "b200", "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if wl.dtype == torch.bfloat16 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[args.workload], "global_batch": bsz * world,
