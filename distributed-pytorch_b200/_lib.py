@@ -11,7 +11,7 @@ import os
 from ._build import LIB_PATH
 
 # constants mirrored from include/b200ddp.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_WORLD = 8
 HANDLE_BYTES = 128
 F32, BF16, F16 = 0, 1, 2
@@ -37,11 +37,13 @@ SYMBOLS = [
     ("b200ddp_last_error", C.c_char_p, [_vp]),
     ("b200ddp_flatten_scale", _i, [_vp, _pp, _pu64, _pu64, _i, _i, _u64, _f, _vp]),
     ("b200ddp_unflatten", _i, [_vp, _pp, _pu64, _pu64, _i, _i, _u64, _vp]),
-    ("b200ddp_allreduce", _i, [_vp, _u64, _u64, _u64, _i, _i, _i, _vp]),
+    ("b200ddp_allreduce", _i, [_vp, _u64, _u64, _u64, _i, _i, _i, _f, _vp]),
     ("b200ddp_fused_bucket", _i, [_vp, _pp, _pu64, _pu64, _i, _i, _u64, _u64, _f, _vp]),
     ("b200ddp_max_table_tensors", _i, []),
     ("b200ddp_fused_max_bytes", _u64, []),
     ("b200ddp_fused_region_bytes", _u64, [_vp, _u64]),
+    ("b200ddp_fused_region_bytes_for", _u64, [_i, _u64]),
+    ("b200ddp_peer_read", _i, [_vp, _i, _u64, _u64, _u64, _i, _vp]),
     ("b200ddp_clear", _i, [_vp, _u64, _u64, _vp]),
     ("b200ddp_broadcast", _i, [_vp, _u64, _u64, _i, _i, _vp]),
     ("b200ddp_barrier", _i, [_vp, _vp]),

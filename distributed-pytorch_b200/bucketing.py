@@ -132,8 +132,3 @@ class BucketLayout:
             self.total_bytes += _round_up(spec.nbytes, self.REGION_ALIGN)
         else:
             spec.out_off = spec.arena_off
-
-    @staticmethod
-    def worst_case_bytes(bucket_nbytes: Sequence[int]) -> int:
-        """Upper bound of the arena any bucketing of these sizes can need (every bucket out of place)."""
-        return sum(2 * _round_up(n, BucketLayout.REGION_ALIGN) for n in bucket_nbytes)

@@ -152,8 +152,8 @@ class P2PComm:
             _lib.check(rc, self._ctx, "unflatten")
 
     def allreduce(self, in_off: int, out_off: int, nbytes: int, dtype: int, algo: int, max_ctas: int,
-                  stream: int) -> None:
-        rc = self._lib.b200ddp_allreduce(self._ctx, in_off, out_off, nbytes, dtype, algo, max_ctas, stream)
+                  stream: int, scale: float = 1.0) -> None:
+        rc = self._lib.b200ddp_allreduce(self._ctx, in_off, out_off, nbytes, dtype, algo, max_ctas, scale, stream)
         if rc:
             _lib.check(rc, self._ctx, "allreduce")
 
@@ -168,6 +168,10 @@ class P2PComm:
         rc = self._lib.b200ddp_broadcast(self._ctx, off, nbytes, root, max_ctas, stream)
         if rc:
             _lib.check(rc, self._ctx, "broadcast")
+
+    def peer_read(self, peer: int, src_off: int, dst_off: int, nbytes: int, stream: int, max_ctas: int = 0) -> None:
+        _lib.check(self._lib.b200ddp_peer_read(self._ctx, peer, src_off, dst_off, nbytes, max_ctas, stream),
+                   self._ctx, "peer_read")
 
     def fused_region_bytes(self, bucket_bytes: int) -> int:
         return int(self._lib.b200ddp_fused_region_bytes(self._ctx, bucket_bytes))

@@ -641,7 +641,11 @@ int copy_bucket(b200ddp_ctx* c, const void* const* ptrs, const uint64_t* off_el,
     if (rc) return rc;
     rc = check_range(c, unflatten ? "unflatten" : "flatten_scale", bucket_off, uint64_t(ve) * 16);
     if (rc) return rc;
-    RT_CHECK(c, launch_flatten(tt, bucket, vb, ve, dtype, scale, unflatten, static_cast<cudaStream_t>(stream)));
+    // an unflatten after a peer timeout must not scatter a partial sum: it checks the rank's sticky poison word
+    const uint32_t* poison = (unflatten && c->world > 1)
+                                 ? reinterpret_cast<const uint32_t*>(static_cast<unsigned char*>(c->base) + kFlagBytes + kEpochBytes)
+                                 : nullptr;
+    RT_CHECK(c, launch_flatten(tt, bucket, vb, ve, dtype, scale, unflatten, poison, static_cast<cudaStream_t>(stream)));
     c->launches++;
   }
   return 0;
@@ -666,6 +670,9 @@ uint64_t b200ddp_fused_region_bytes(b200ddp_ctx* c, uint64_t bucket_bytes) {
   return c ? fused_region_bytes((bucket_bytes + 15) / 16 * 16, c->world) : 0;
 }
 uint64_t b200ddp_fused_max_bytes(void) { return kFusedMaxBytes; }
+uint64_t b200ddp_fused_region_bytes_for(int world, uint64_t bucket_bytes) {
+  return fused_region_bytes((bucket_bytes + 15) / 16 * 16, world);
+}
 
 const char* b200ddp_last_error(b200ddp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
 
@@ -938,7 +945,7 @@ int b200ddp_pick_algo(b200ddp_ctx* c, uint64_t nbytes) {
 }
 
 int b200ddp_allreduce(b200ddp_ctx* c, uint64_t in_off, uint64_t out_off, uint64_t nbytes, int dtype, int algo,
-                      int max_ctas, void* stream) {
+                      int max_ctas, float scale, void* stream) {
   int rc = check_ready(c);
   if (rc) return rc;
   if (algo == B200DDP_ALGO_AUTO) algo = b200ddp_pick_algo(c, nbytes);
@@ -953,9 +960,21 @@ int b200ddp_allreduce(b200ddp_ctx* c, uint64_t in_off, uint64_t out_off, uint64_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint64_t nvec = nbytes / 16;
   unsigned char* arena = static_cast<unsigned char*>(c->base) + kSignalBytes;
+  if (!(scale == scale) || scale == 0.0f) return fail(c, B200DDP_EINVAL, "allreduce: scale must be a non-zero number");
   if (c->world == 1) {
-    if (in_off != out_off) {
-      RT_CHECK(c, launch_local_copy(arena + out_off, arena + in_off, nvec, s));
+    if (scale != 1.0f) {
+      // a world of one still owes the caller out = scale * in: one flatten launch over the region as one tensor
+      TensorTable tt{};
+      tt.n = 1;
+      tt.ptr[0] = reinterpret_cast<uint64_t>(arena + in_off);
+      tt.len_el[0] = nbytes / dtype_size(dtype);
+      tt.off_vec[0] = 0;
+      tt.off_vec[1] = static_cast<uint32_t>(nvec);
+      if (nvec > 0xffffffffull) return fail(c, B200DDP_EINVAL, "bucket larger than 64 GiB");
+      RT_CHECK(c, launch_flatten(tt, arena + out_off, 0, static_cast<uint32_t>(nvec), dtype, scale, false, nullptr, s));
+      c->launches++;
+    } else if (in_off != out_off) {
+      RT_CHECK(c, launch_local_copy(arena + out_off, arena + in_off, nvec, 0, s));
       c->launches++;
     }
     return 0;
@@ -964,17 +983,18 @@ int b200ddp_allreduce(b200ddp_ctx* c, uint64_t in_off, uint64_t out_off, uint64_
   switch (algo) {
     case B200DDP_ALGO_ONESHOT:
       if (in_off == out_off) return fail(c, B200DDP_EINVAL, "one-shot allreduce must be out of place");
-      RT_CHECK(c, launch_oneshot(c->pt, ctl, in_off, out_off, nvec, dtype, max_ctas, s));
+      RT_CHECK(c, launch_oneshot(c->pt, ctl, in_off, out_off, nvec, dtype, max_ctas, scale, s));
       break;
     case B200DDP_ALGO_TWOSHOT:
-      RT_CHECK(c, launch_twoshot(c->pt, ctl, in_off, out_off, nvec, dtype, max_ctas, s));
+      RT_CHECK(c, launch_twoshot(c->pt, ctl, in_off, out_off, nvec, dtype, max_ctas, scale, s));
       break;
     case B200DDP_ALGO_TWOSHOT_TMA:
-      RT_CHECK(c, launch_twoshot_tma(c->pt, ctl, in_off, out_off, nvec, dtype, max_ctas, s));
+      RT_CHECK(c, launch_twoshot_tma(c->pt, ctl, in_off, out_off, nvec, dtype, max_ctas, scale, s));
       break;
     case B200DDP_ALGO_NVLS:
       if (!c->has_mc) return fail(c, B200DDP_EUNSUP, "NVLS requested but no multicast mapping exists");
-      RT_CHECK(c, launch_nvls(c->pt, ctl, static_cast<uint64_t>(c->mc_va), in_off, out_off, nvec, dtype, max_ctas, s));
+      RT_CHECK(c, launch_nvls(c->pt, ctl, static_cast<uint64_t>(c->mc_va), in_off, out_off, nvec, dtype, max_ctas, scale,
+                              s));
       break;
     default:
       return fail(c, B200DDP_EINVAL, "unknown algorithm %d", algo);
@@ -1017,6 +1037,23 @@ int b200ddp_broadcast(b200ddp_ctx* c, uint64_t off, uint64_t nbytes, int root, i
   if (c->world == 1 || nbytes == 0) return 0;
   DeviceGuard g(c->device);
   RT_CHECK(c, launch_broadcast(c->pt, make_ctl(c), off, nbytes / 16, root, max_ctas, static_cast<cudaStream_t>(stream)));
+  c->launches++;
+  return 0;
+}
+
+int b200ddp_peer_read(b200ddp_ctx* c, int peer, uint64_t src_off, uint64_t dst_off, uint64_t nbytes, int max_ctas,
+                      void* stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (peer < 0 || peer >= c->world) return fail(c, B200DDP_EINVAL, "peer_read: rank %d out of range", peer);
+  if ((rc = check_range(c, "peer_read(src)", src_off, nbytes))) return rc;
+  if ((rc = check_range(c, "peer_read(dst)", dst_off, nbytes))) return rc;
+  if (nbytes == 0) return 0;
+  DeviceGuard g(c->device);
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(c->pt.base[peer]) + kSignalBytes + src_off;
+  unsigned char* dst = static_cast<unsigned char*>(c->base) + kSignalBytes + dst_off;
+  RT_CHECK(c, launch_local_copy(dst, src, nbytes / 16, max_ctas, static_cast<cudaStream_t>(stream)));
   c->launches++;
   return 0;
 }

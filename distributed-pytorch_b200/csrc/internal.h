@@ -29,8 +29,9 @@ constexpr uint64_t fused_region_bytes(uint64_t bucket_bytes, int ws) {
 //   [kFlagBytes, +kEpochBytes)   uint32 epoch[kMaxBlocks]             local, per-CTA barrier generation
 constexpr uint64_t kFlagBytes = uint64_t(kMaxBlocks) * kMaxWorld * 4;
 constexpr uint64_t kEpochBytes = uint64_t(kMaxBlocks) * 4;
+//   [kFlagBytes + kEpochBytes]   uint32 poisoned                      local, sticky: a kernel timed out on a peer
 constexpr uint64_t kSignalBytes = 2u << 20;  // one 2 MiB page: keeps the arena 2 MiB aligned
-static_assert(kFlagBytes + kEpochBytes <= kSignalBytes, "signal region too small");
+static_assert(kFlagBytes + kEpochBytes + 4 <= kSignalBytes, "signal region too small");
 
 // Base addresses of every rank's shared allocation as mapped into THIS process.
 struct PeerTable {
@@ -55,27 +56,27 @@ struct TensorTable {
   int32_t n;
 };
 
-struct LaunchCfg {
-  int max_ctas;  // 0 = default
-};
-
 // kernels.cu — launch wrappers.  All return cudaError_t from the launch.
+// `poison`: the rank's sticky timeout word (device pointer) — an unflatten launch returns without writing when
+// it is set; nullptr = no check
 cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_begin, uint32_t vec_end, int dtype,
-                           float scale, bool unflatten, cudaStream_t s);
+                           float scale, bool unflatten, const uint32_t* poison, cudaStream_t s);
 cudaError_t launch_oneshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
-                           int dtype, int max_ctas, cudaStream_t s);
+                           int dtype, int max_ctas, float scale, cudaStream_t s);
+// `scale` multiplies the reduced sum before it is written back (1.0 = none; the Reducer pre-scales in flatten
+// like the reference, the comm-hook shim and in-place buckets post-scale here)
 cudaError_t launch_twoshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
-                           int dtype, int max_ctas, cudaStream_t s);
+                           int dtype, int max_ctas, float scale, cudaStream_t s);
 cudaError_t launch_twoshot_tma(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off,
-                               uint64_t nvec, int dtype, int max_ctas, cudaStream_t s);
+                               uint64_t nvec, int dtype, int max_ctas, float scale, cudaStream_t s);
 cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, uint64_t in_off, uint64_t out_off,
-                        uint64_t nvec, int dtype, int max_ctas, cudaStream_t s);
+                        uint64_t nvec, int dtype, int max_ctas, float scale, cudaStream_t s);
 cudaError_t launch_fused(const TensorTable& tt, const PeerTable& pt, const Ctl& ctl, uint64_t bucket_off,
                          uint32_t nvec, int dtype, float scale, cudaStream_t s);
 cudaError_t launch_broadcast(const PeerTable& pt, const Ctl& ctl, uint64_t off, uint64_t nvec, int root,
                              int max_ctas, cudaStream_t s);
 cudaError_t launch_barrier(const PeerTable& pt, const Ctl& ctl, cudaStream_t s);
-cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, cudaStream_t s);
+cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, int max_ctas, cudaStream_t s);
 cudaError_t prepare_kernels(int world);  // dynamic-smem opt-in + eager load of every kernel of this world size
 
 }  // namespace b200ddp

@@ -178,14 +178,33 @@ __device__ __forceinline__ void write_epoch(const PeerTable& pt, const Ctl& ctl,
   if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(epoch_slot(pt.base[ctl.rank], blockIdx.x)) = e;
 }
 
-// Every thread of the CTA calls this.  On return all CTAs with this blockIdx on all ranks have arrived
+// Sticky per-rank "poisoned" word (device memory, local signal region): set by the first kernel of this rank
+// that times out on a peer.  Later collective kernels return at once and unflatten launches leave the
+// gradients untouched, so a half-reduced bucket is never scattered into .grad; the host sees the mapped error
+// word (b200ddp_poll_error) and raises.
+__device__ __forceinline__ uint32_t* poison_slot(uint64_t base) {
+  return reinterpret_cast<uint32_t*>(base + kFlagBytes + kEpochBytes);
+}
+__device__ __forceinline__ bool poisoned(const PeerTable& pt, const Ctl& ctl) {
+  return *reinterpret_cast<volatile uint32_t*>(poison_slot(pt.base[ctl.rank])) != 0u;
+}
+__device__ __forceinline__ void raise_timeout(const PeerTable& pt, const Ctl& ctl, int peer) {
+  *reinterpret_cast<volatile uint32_t*>(poison_slot(pt.base[ctl.rank])) = 1u;
+  *reinterpret_cast<volatile uint32_t*>(ctl.err) = 1u + static_cast<uint32_t>(peer);
+}
+
+// Every thread of the CTA calls this.  On return (true) all CTAs with this blockIdx on all ranks have arrived
 // with `target`, and the writes (local and peer) every thread of those CTAs made before arriving are
 // visible to this CTA.  Ordering: the CTA's writes happen-before the bar.sync, the per-peer thread's
 // st.release.sys is cumulative over them (PTX memory model, causality order through the CTA barrier), the
 // waiter's ld.acquire.sys + bar.sync extends that to every thread here — the same pattern as the
 // block barriers of NCCL's and TensorRT-LLM's one/two-shot kernels.
-__device__ __forceinline__ void cta_barrier(const PeerTable& pt, const Ctl& ctl, int ws, uint32_t target) {
+// Returns false (to every thread of the CTA) when a peer did not arrive within the timeout: the error word in
+// mapped host memory is set and the caller must NOT touch gradients or peer data any more (a poisoned
+// bucket is left as it was instead of being overwritten with a partial sum).
+__device__ __forceinline__ bool cta_barrier(const PeerTable& pt, const Ctl& ctl, int ws, uint32_t target) {
   __syncthreads();
+  int ok = 1;
   if (threadIdx.x < ws) {
     const int q = threadIdx.x;
     st_release_sys(flag_slot(pt.base[q], blockIdx.x, ctl.rank), target);
@@ -197,13 +216,14 @@ __device__ __forceinline__ void cta_barrier(const PeerTable& pt, const Ctl& ctl,
         const uint64_t now = globaltimer_ns();
         if (t0 == 0) t0 = now;
         if (now - t0 > ctl.timeout_ns) {
-          *reinterpret_cast<volatile uint32_t*>(ctl.err) = 1u + static_cast<uint32_t>(q);
+          raise_timeout(pt, ctl, q);
+          ok = 0;
           break;
         }
       }
     }
   }
-  __syncthreads();
+  return __syncthreads_and(ok) != 0;
 }
 
 __device__ __forceinline__ uint64_t arena_of(const PeerTable& pt, int q) { return pt.base[q] + kSignalBytes; }
@@ -285,49 +305,56 @@ __device__ __forceinline__ void scatter_vec(const SmemTable& s, int t, uint32_t 
 }
 
 constexpr int kCopyThreads = 512;
-constexpr int kCopyUnroll = 4;
-constexpr uint32_t kCopyTile = kCopyThreads * kCopyUnroll;  // vectors per tile = 32 KiB
 
 // One launch moves bucket vectors [vec_begin, vec_end) (all inside the tensors of `tt`).
 // HBM-bound: reads S + writes S bytes for S bytes of gradients.
-template <int DT, bool UNFLATTEN>
-__global__ void __launch_bounds__(kCopyThreads, 4)  // <= 32 registers: 4 CTAs = 2048 threads per SM
+// A tile is kCopyThreads * UNROLL vectors; every thread keeps UNROLL 16-byte loads in flight before its first
+// store.  Tiles that lie inside one aligned tensor take a straight vector copy; tiles that span tensor
+// boundaries (ResNet-50: 107 of 161 gradients are < 16 KiB), tails or unaligned storage look the tensor of every
+// vector up in the shared-memory table (binary search over the <= few tensors of the tile) but keep the same
+// loads-then-stores structure, so such a tile costs one memory round trip like any other (round 1 walked it
+// one dependent vector at a time and those tiles finished last: 0.44 of the HBM roofline on ResNet-50 buckets).
+template <int DT, bool UNFLATTEN, int UNROLL>
+__global__ void __launch_bounds__(kCopyThreads, UNROLL <= 4 ? 4 : 2)
 multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* __restrict__ bucket,
-                         uint32_t vec_begin, uint32_t vec_end, float scale, int even_split) {
+                         uint32_t vec_begin, uint32_t vec_end, float scale, int even_split,
+                         const uint32_t* __restrict__ poison) {
+  constexpr uint32_t kTile = kCopyThreads * UNROLL;
   __shared__ SmemTable s;
+  // unflatten after a peer timeout: the bucket may hold a partial sum, leave the gradients alone
+  if (UNFLATTEN && poison != nullptr && *reinterpret_cast<const volatile uint32_t*>(poison) != 0u) return;
   load_table(s, tt);
   const int n = tt.n;
-  // The grid is one co-resident wave (launch_flatten).  Default: 32 KiB tiles dealt round-robin (the CTAs
-  // sweep memory as a sliding window).  even_split: every CTA owns one contiguous, equal share instead —
-  // no tail, but measurably worse DRAM locality (see launch_flatten).
+  // The grid is one co-resident wave (launch_flatten).  Default: tiles dealt round-robin (the CTAs sweep
+  // memory as a sliding window).  even_split: every CTA owns one contiguous, equal share instead — no tail,
+  // but measurably worse DRAM locality (see launch_flatten).
   const uint32_t granules = (vec_end - vec_begin + kCopyThreads - 1) / kCopyThreads;
   const uint32_t per = granules / gridDim.x, extra = granules % gridDim.x;
   const uint32_t g0 = blockIdx.x * per + min(blockIdx.x, extra);
   const uint32_t g1 = g0 + per + (blockIdx.x < extra ? 1u : 0u);
-  // even_split == 0: tiles are dealt round-robin instead (CTAs sweep memory as a sliding window)
-  const uint32_t r0 = even_split ? vec_begin + g0 * kCopyThreads : vec_begin + blockIdx.x * kCopyTile;
+  const uint32_t r0 = even_split ? vec_begin + g0 * kCopyThreads : vec_begin + blockIdx.x * kTile;
   const uint32_t r1 = even_split ? min(vec_end, vec_begin + g1 * kCopyThreads) : vec_end;
-  const uint32_t stride = even_split ? kCopyTile : gridDim.x * kCopyTile;
+  const uint32_t stride = even_split ? kTile : gridDim.x * kTile;
   uint4* bvec = reinterpret_cast<uint4*>(bucket);
   for (uint32_t v0 = r0; v0 < r1; v0 += stride) {
-    const uint32_t v1 = min(v0 + kCopyTile, r1);
+    const uint32_t v1 = min(v0 + kTile, r1);
     const int t_lo = locate(s.off, 0, n - 1, v0);
     const int t_hi = locate(s.off, t_lo, n - 1, v1 - 1);
     const uint64_t first = static_cast<uint64_t>(v0 - s.off[t_lo]);
     const bool fast = (t_lo == t_hi) && ((s.ptr[t_lo] & 15) == 0) &&
                       (static_cast<uint64_t>(v1 - s.off[t_lo]) * Vec<DT>::N <= s.len[t_lo]);
+    uint4 x[UNROLL];
     if (fast) {
-      // whole tile inside one aligned tensor: straight vector copy, kCopyUnroll loads in flight/thread
+      // whole tile inside one aligned tensor: straight vector copy
       uint4* tvec = reinterpret_cast<uint4*>(s.ptr[t_lo]) + first;
       const uint32_t cnt = v1 - v0;
-      uint4 x[kCopyUnroll];
 #pragma unroll
-      for (int j = 0; j < kCopyUnroll; ++j) {
+      for (int j = 0; j < UNROLL; ++j) {
         const uint32_t i = threadIdx.x + j * kCopyThreads;
         if (i < cnt) x[j] = UNFLATTEN ? ld_vec(bvec + v0 + i) : ld_vec(tvec + i);
       }
 #pragma unroll
-      for (int j = 0; j < kCopyUnroll; ++j) {
+      for (int j = 0; j < UNROLL; ++j) {
         const uint32_t i = threadIdx.x + j * kCopyThreads;
         if (i < cnt) {
           if (UNFLATTEN)
@@ -336,24 +363,54 @@ multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* 
             st_vec(bvec + v0 + i, scale_vec<DT>(x[j], scale));
         }
       }
+    } else if (UNFLATTEN) {
+      // bucket-side loads do not depend on the tensor lookup: issue them all, search while they fly
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const uint32_t v = v0 + threadIdx.x + j * kCopyThreads;
+        if (v < v1) x[j] = ld_vec(bvec + v);
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const uint32_t v = v0 + threadIdx.x + j * kCopyThreads;
+        if (v < v1) scatter_vec<DT>(s, locate(s.off, t_lo, t_hi, v), v, x[j]);
+      }
     } else {
-      // tile spans tensor boundaries (many small tensors), tails or unaligned storage
-#pragma unroll 1
-      for (uint32_t v = v0 + threadIdx.x; v < v1; v += kCopyThreads) {
-        const int t = locate(s.off, t_lo, t_hi, v);
-        if (UNFLATTEN)
-          scatter_vec<DT>(s, t, v, ld_vec(bvec + v));
-        else
-          st_vec(bvec + v, scale_vec<DT>(gather_vec<DT>(s, t, v), scale));
+      int t[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const uint32_t v = v0 + threadIdx.x + j * kCopyThreads;
+        t[j] = v < v1 ? locate(s.off, t_lo, t_hi, v) : t_lo;
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const uint32_t v = v0 + threadIdx.x + j * kCopyThreads;
+        if (v < v1) x[j] = gather_vec<DT>(s, t[j], v);
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        const uint32_t v = v0 + threadIdx.x + j * kCopyThreads;
+        if (v < v1) st_vec(bvec + v, scale_vec<DT>(x[j], scale));
       }
     }
   }
 }
 
+// plain vector copy, 4 loads in flight per thread (world-1 out-of-place "allreduce", and the peer-read
+// bandwidth probe: src may be a peer's mapping, then the loads cross NVLink)
 __global__ void __launch_bounds__(512) local_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
                                                          uint64_t nvec) {
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < nvec; i += uint64_t(gridDim.x) * blockDim.x)
-    st_vec(dst + i, ld_vec(src + i));
+  constexpr int U = 4;
+  const uint64_t step = uint64_t(gridDim.x) * blockDim.x * U;
+  for (uint64_t i0 = blockIdx.x * uint64_t(blockDim.x) * U + threadIdx.x; i0 < nvec; i0 += step) {
+    uint4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + uint64_t(u) * blockDim.x < nvec) x[u] = ld_vec(src + i0 + uint64_t(u) * blockDim.x);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + uint64_t(u) * blockDim.x < nvec) st_vec(dst + i0 + uint64_t(u) * blockDim.x, x[u]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -364,9 +421,10 @@ constexpr int kArThreads = 512;
 template <int DT, int WS>
 __global__ void __launch_bounds__(kArThreads)
 oneshot_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t in_off,
-               uint64_t out_off, uint64_t nvec) {
+               uint64_t out_off, uint64_t nvec, float scale) {
+  if (poisoned(pt, ctl)) return;
   const uint32_t e = read_epoch(pt, ctl);
-  cta_barrier(pt, ctl, WS, e + 1);
+  if (!cta_barrier(pt, ctl, WS, e + 1)) return;
   const uint4* in[WS];
 #pragma unroll
   for (int q = 0; q < WS; ++q) in[q] = reinterpret_cast<const uint4*>(arena_of(pt, q) + in_off);
@@ -375,7 +433,7 @@ oneshot_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl
     uint4 x[WS];
 #pragma unroll
     for (int q = 0; q < WS; ++q) x[q] = ld_vec(in[q] + i);
-    st_vec(out + i, reduce_vecs<DT, WS>(x));
+    st_vec(out + i, scale_vec<DT>(reduce_vecs<DT, WS>(x), scale));
   }
   cta_barrier(pt, ctl, WS, e + 2);
   write_epoch(pt, ctl, e + 2);
@@ -392,9 +450,10 @@ constexpr int kTwoShotUnroll = 2;
 template <int DT, int WS>
 __global__ void __launch_bounds__(kArThreads)
 twoshot_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t in_off,
-               uint64_t out_off, uint64_t nvec) {
+               uint64_t out_off, uint64_t nvec, float scale) {
+  if (poisoned(pt, ctl)) return;
   const uint32_t e = read_epoch(pt, ctl);
-  cta_barrier(pt, ctl, WS, e + 1);
+  if (!cta_barrier(pt, ctl, WS, e + 1)) return;
   const uint64_t slice = (nvec + WS - 1) / WS;
   const uint64_t begin = min(nvec, slice * ctl.rank);
   const uint64_t end = min(nvec, begin + slice);
@@ -420,7 +479,7 @@ twoshot_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl
     for (int u = 0; u < kTwoShotUnroll; ++u) {
       const uint64_t i = i0 + uint64_t(u) * kArThreads;
       if (i < end) {
-        const uint4 r = reduce_vecs<DT, WS>(x[u]);
+        const uint4 r = scale_vec<DT>(reduce_vecs<DT, WS>(x[u]), scale);
 #pragma unroll
         for (int q = 0; q < WS; ++q) st_vec(out[q] + i, r);
       }
@@ -471,7 +530,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 template <int DT, int WS>
 __global__ void __launch_bounds__(kTmaThreads)
 twoshot_tma_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t in_off,
-                   uint64_t out_off, uint64_t nvec) {
+                   uint64_t out_off, uint64_t nvec, float scale) {
+  if (poisoned(pt, ctl)) return;
   constexpr int STAGES = tma_stages(WS);
   extern __shared__ __align__(128) unsigned char ring[];  // STAGES * WS * 4 KiB
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -490,7 +550,7 @@ twoshot_tma_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t e = read_epoch(pt, ctl);
-  cta_barrier(pt, ctl, WS, e + 1);  // also publishes the mbarrier inits (contains __syncthreads)
+  if (!cta_barrier(pt, ctl, WS, e + 1)) return;  // also publishes the mbarrier inits (contains __syncthreads)
 
   const uint64_t slice = (nvec + WS - 1) / WS;
   const uint64_t begin = min(nvec, slice * ctl.rank);
@@ -499,6 +559,9 @@ twoshot_tma_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
+      // the peers' flatten writes were observed through the generic proxy (ld.acquire.sys in cta_barrier); the
+      // bulk copies below read them through the async proxy: order the two proxies explicitly
+      asm volatile("fence.proxy.async.global;" ::: "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -532,7 +595,7 @@ twoshot_tma_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__
         uint4 x[WS];
 #pragma unroll
         for (int q = 0; q < WS; ++q) x[q] = lds_vec(ring_s + (stage * WS + q) * kTmaChunkBytes + ctid * 16);
-        const uint4 r = reduce_vecs<DT, WS>(x);
+        const uint4 r = scale_vec<DT>(reduce_vecs<DT, WS>(x), scale);
 #pragma unroll
         for (int q = 0; q < WS; ++q) st_vec(out[q] + v0 + ctid, r);
       }
@@ -592,10 +655,11 @@ __device__ __forceinline__ void multimem_st(void* p, const uint4& v) {
 template <int DT, int kNvlsUnroll>
 __global__ void __launch_bounds__(kArThreads)
 nvls_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t mc_base, uint64_t in_off,
-            uint64_t out_off, uint64_t nvec) {
+            uint64_t out_off, uint64_t nvec, float scale) {
+  if (poisoned(pt, ctl)) return;
   const int ws = ctl.world;
   const uint32_t e = read_epoch(pt, ctl);
-  cta_barrier(pt, ctl, ws, e + 1);
+  if (!cta_barrier(pt, ctl, ws, e + 1)) return;
   const uint64_t slice = (nvec + ws - 1) / ws;
   const uint64_t begin = min(nvec, slice * ctl.rank);
   const uint64_t end = min(nvec, begin + slice);
@@ -612,7 +676,7 @@ nvls_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ct
 #pragma unroll
     for (int u = 0; u < kNvlsUnroll; ++u) {
       const uint64_t i = i0 + uint64_t(u) * kArThreads;
-      if (i < end) multimem_st(out + i, x[u]);
+      if (i < end) multimem_st(out + i, scale_vec<DT>(x[u], scale));
     }
   }
   cta_barrier(pt, ctl, ws, e + 2);
@@ -650,6 +714,7 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
     }
     return;
   }
+  if (poisoned(pt, ctl)) return;
   const uint32_t e = read_epoch(pt, ctl);
   const uint64_t slot_off = bucket_off + ((e >> 1) & 1u) * (static_cast<uint64_t>(nvec) * 16);
   uint4* mine = reinterpret_cast<uint4*>(arena_of(pt, ctl.rank) + slot_off);
@@ -657,7 +722,7 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
     const int t = locate(s.off, 0, n - 1, v);
     st_vec(mine + v, scale_vec<DT>(gather_vec<DT>(s, t, v), scale));
   }
-  cta_barrier(pt, ctl, WS, e + 1);
+  if (!cta_barrier(pt, ctl, WS, e + 1)) return;  // gradients keep their local values
   const uint4* in[WS];
 #pragma unroll
   for (int q = 0; q < WS; ++q) in[q] = reinterpret_cast<const uint4*>(arena_of(pt, q) + slot_off);
@@ -739,6 +804,7 @@ __global__ void __launch_bounds__(kLLThreads)
 fused_ll_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ PeerTable pt,
                 const __grid_constant__ Ctl ctl, uint64_t ll_off, uint32_t nwords, float scale) {
   __shared__ SmemTable s;
+  if (poisoned(pt, ctl)) return;
   const uint32_t e = read_epoch(pt, ctl);  // before the barrier inside load_table: thread 0 rewrites it at the end
   load_table(s, tt);
   const int n = tt.n;
@@ -754,30 +820,49 @@ fused_ll_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ 
 #pragma unroll
     for (int q = 0; q < WS; ++q) st_ll(reinterpret_cast<uint2*>(arena_of(pt, q) + ll_off) + slot, d, tag);
   }
-  // pull: poll my own slots of every source rank, sum in rank order, scatter
+  // pull: poll my own slots of every source rank until all ws tags match this generation; the data words that
+  // travelled with the tags stay in registers (a thread owns at most kLLWordsPerCta / kLLThreads words)
+  constexpr int kPerThread = kLLWordsPerCta / kLLThreads;
   const uint2* mine = reinterpret_cast<const uint2*>(arena_of(pt, ctl.rank) + ll_off) + set_base;
-  for (uint32_t w = w_begin + threadIdx.x; w < w_end; w += kLLThreads) {
-    uint4 x[WS];
-    uint64_t t0 = 0;
-    uint32_t spins = 0;
+  uint32_t val[kPerThread][WS];
+  int timed_out = 0;
 #pragma unroll
-    for (int q = 0; q < WS; ++q) {
-      uint2 r = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
-      while (r.y != tag) {
-        if ((++spins & 255u) == 0) {
-          const uint64_t now = globaltimer_ns();
-          if (t0 == 0) t0 = now;
-          if (now - t0 > ctl.timeout_ns) {
-            *reinterpret_cast<volatile uint32_t*>(ctl.err) = 1u + static_cast<uint32_t>(q);
-            break;
+  for (int k = 0; k < kPerThread; ++k) {
+    const uint32_t w = w_begin + threadIdx.x + k * kLLThreads;
+    if (w < w_end && !timed_out) {
+      uint64_t t0 = 0;
+      uint32_t spins = 0;
+#pragma unroll
+      for (int q = 0; q < WS; ++q) {
+        uint2 r = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
+        while (r.y != tag && !timed_out) {
+          if ((++spins & 255u) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > ctl.timeout_ns) {
+              raise_timeout(pt, ctl, q);
+              timed_out = 1;
+            }
           }
+          r = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
         }
-        r = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
+        val[k][q] = r.x;
       }
-      x[q] = make_uint4(r.x, 0, 0, 0);
     }
-    const int t = locate(s.off, 0, n - 1, w >> 2);
-    scatter_word<DT>(s, t, w, reduce_vecs<DT, WS>(x).x);
+  }
+  // a bucket that did not arrive completely is not scattered at all: the gradients keep their local values
+  if (__syncthreads_or(timed_out)) return;
+  // sum in rank order, scatter
+#pragma unroll
+  for (int k = 0; k < kPerThread; ++k) {
+    const uint32_t w = w_begin + threadIdx.x + k * kLLThreads;
+    if (w < w_end) {
+      uint4 x[WS];
+#pragma unroll
+      for (int q = 0; q < WS; ++q) x[q] = make_uint4(val[k][q], 0, 0, 0);
+      const int t = locate(s.off, 0, n - 1, w >> 2);
+      scatter_word<DT>(s, t, w, reduce_vecs<DT, WS>(x).x);
+    }
   }
   write_epoch(pt, ctl, e + 2);
 }
@@ -788,9 +873,10 @@ fused_ll_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ 
 __global__ void __launch_bounds__(kArThreads)
 broadcast_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ctl, uint64_t off, uint64_t nvec,
                  int root) {
+  if (poisoned(pt, ctl)) return;
   const int ws = ctl.world;
   const uint32_t e = read_epoch(pt, ctl);
-  cta_barrier(pt, ctl, ws, e + 1);
+  if (!cta_barrier(pt, ctl, ws, e + 1)) return;
   if (ctl.rank == root) {
     const uint4* src = reinterpret_cast<const uint4*>(arena_of(pt, root) + off);
     for (uint64_t i = blockIdx.x * uint64_t(kArThreads) + threadIdx.x; i < nvec;
@@ -806,6 +892,7 @@ broadcast_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ C
 
 __global__ void __launch_bounds__(32) barrier_kernel(const __grid_constant__ PeerTable pt,
                                                      const __grid_constant__ Ctl ctl) {
+  if (poisoned(pt, ctl)) return;
   const uint32_t e = read_epoch(pt, ctl);
   cta_barrier(pt, ctl, ctl.world, e + 1);
   write_epoch(pt, ctl, e + 2);
@@ -863,67 +950,95 @@ inline int clamp_grid(uint64_t want, int max_ctas, int dflt) {
 // ---------------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------
-cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_begin, uint32_t vec_end, int dtype,
-                           float scale, bool unflatten, cudaStream_t s) {
-  if (vec_end <= vec_begin || tt.n <= 0) return cudaSuccess;
-  // one co-resident wave: 4 CTAs of 512 threads per SM (__launch_bounds__(512, 4), 32 registers, no spills)
+namespace {
+// Vectors per thread and tile of the copy kernel (B200DDP_COPY_UNROLL = 2 | 4 | 8 forces one).  Measured on B200
+// (tools/ab_copy.py, profiles/): 4 x 16 B in flight per thread at 4 CTAs x 512 threads per SM.
+int copy_unroll() {
+  static const int u = [] {
+    const char* e = getenv("B200DDP_COPY_UNROLL");
+    const int v = e ? atoi(e) : 4;
+    return (v == 2 || v == 8) ? v : 4;
+  }();
+  return u;
+}
+
+template <int DT, int UNROLL>
+void launch_copy_variant(const TensorTable& tt, unsigned char* b, uint32_t vec_begin, uint32_t vec_end, float scale,
+                         bool unflatten, int even, const uint32_t* poison, cudaStream_t s) {
+  // one co-resident wave: 4 CTAs of 512 threads per SM up to UNROLL 4 (32 registers), 2 per SM at UNROLL 8
   const uint32_t granules = (vec_end - vec_begin + kCopyThreads - 1) / kCopyThreads;
-  const int grid = static_cast<int>(granules < uint32_t(kNumSMs * 4) ? granules : uint32_t(kNumSMs * 4));
+  const uint32_t wave = uint32_t(kNumSMs) * (UNROLL <= 4 ? 4 : 2);
+  const int grid = static_cast<int>(granules < wave ? granules : wave);
+  if (unflatten)
+    multi_tensor_copy_kernel<DT, true, UNROLL>
+        <<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even, poison);
+  else
+    multi_tensor_copy_kernel<DT, false, UNROLL>
+        <<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even, nullptr);
+}
+}  // namespace
+
+cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_begin, uint32_t vec_end, int dtype,
+                           float scale, bool unflatten, const uint32_t* poison, cudaStream_t s) {
+  if (vec_end <= vec_begin || tt.n <= 0) return cudaSuccess;
   unsigned char* b = static_cast<unsigned char*>(bucket);
-  // Work split, A/B-measured on one box (tools/ab_copy.py): dealing 32 KiB tiles round-robin makes the
-  // co-resident CTAs sweep memory as a sliding window and beat an even per-CTA split by 2-7 % at 16-256 MiB
-  // (25 MiB: 4.88 vs 4.58 TB/s), so it is the default; B200DDP_COPY_SPLIT=even selects the other.
+  // Work split, A/B-measured on one box (tools/ab_copy.py): dealing tiles round-robin makes the co-resident
+  // CTAs sweep memory as a sliding window and beat an even per-CTA split by 2-7 % at 16-256 MiB (25 MiB:
+  // 4.88 vs 4.58 TB/s), so it is the default; B200DDP_COPY_SPLIT=even selects the other.
   const char* mode = getenv("B200DDP_COPY_SPLIT");
   const int even = (mode && mode[0] == 'e') ? 1 : 0;
+  const int unroll = copy_unroll();
   B200_DISPATCH_DT(dtype, {
-    if (unflatten)
-      multi_tensor_copy_kernel<DT, true><<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even);
+    if (unroll == 2)
+      launch_copy_variant<DT, 2>(tt, b, vec_begin, vec_end, scale, unflatten, even, poison, s);
+    else if (unroll == 8)
+      launch_copy_variant<DT, 8>(tt, b, vec_begin, vec_end, scale, unflatten, even, poison, s);
     else
-      multi_tensor_copy_kernel<DT, false><<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even);
+      launch_copy_variant<DT, 4>(tt, b, vec_begin, vec_end, scale, unflatten, even, poison, s);
   });
   return cudaGetLastError();
 }
 
-cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, cudaStream_t s) {
+cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, int max_ctas, cudaStream_t s) {
   if (nvec == 0) return cudaSuccess;
-  const int grid = clamp_grid((nvec + 2047) / 2048, 0, kNumSMs * 4);
+  const int grid = clamp_grid((nvec + 2047) / 2048, max_ctas, kNumSMs * 4);
   local_copy_kernel<<<grid, 512, 0, s>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), nvec);
   return cudaGetLastError();
 }
 
 cudaError_t launch_oneshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
-                           int dtype, int max_ctas, cudaStream_t s) {
+                           int dtype, int max_ctas, float scale, cudaStream_t s) {
   const int grid = clamp_grid((nvec + kArThreads - 1) / kArThreads, max_ctas, 36);
   B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
-                     oneshot_kernel<DT, WS><<<grid, kArThreads, 0, s>>>(pt, ctl, in_off, out_off, nvec);
+                     oneshot_kernel<DT, WS><<<grid, kArThreads, 0, s>>>(pt, ctl, in_off, out_off, nvec, scale);
                    }));
   return cudaGetLastError();
 }
 
 cudaError_t launch_twoshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
-                           int dtype, int max_ctas, cudaStream_t s) {
+                           int dtype, int max_ctas, float scale, cudaStream_t s) {
   const uint64_t slice = (nvec + ctl.world - 1) / ctl.world;
   const uint64_t step = uint64_t(kArThreads) * kTwoShotUnroll;
   const int grid = clamp_grid((slice + step - 1) / step, max_ctas, 72);
   B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
-                     twoshot_kernel<DT, WS><<<grid, kArThreads, 0, s>>>(pt, ctl, in_off, out_off, nvec);
+                     twoshot_kernel<DT, WS><<<grid, kArThreads, 0, s>>>(pt, ctl, in_off, out_off, nvec, scale);
                    }));
   return cudaGetLastError();
 }
 
 cudaError_t launch_twoshot_tma(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off,
-                               uint64_t nvec, int dtype, int max_ctas, cudaStream_t s) {
+                               uint64_t nvec, int dtype, int max_ctas, float scale, cudaStream_t s) {
   const uint64_t slice = (nvec + ctl.world - 1) / ctl.world;
   const int grid = clamp_grid((slice + kTmaChunkVec - 1) / kTmaChunkVec, max_ctas, 36);
   B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
                      constexpr size_t smem = size_t(tma_stages(WS)) * WS * kTmaChunkBytes;
-                     twoshot_tma_kernel<DT, WS><<<grid, kTmaThreads, smem, s>>>(pt, ctl, in_off, out_off, nvec);
+                     twoshot_tma_kernel<DT, WS><<<grid, kTmaThreads, smem, s>>>(pt, ctl, in_off, out_off, nvec, scale);
                    }));
   return cudaGetLastError();
 }
 
 cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, uint64_t in_off, uint64_t out_off,
-                        uint64_t nvec, int dtype, int max_ctas, cudaStream_t s) {
+                        uint64_t nvec, int dtype, int max_ctas, float scale, cudaStream_t s) {
   const uint64_t slice = (nvec + ctl.world - 1) / ctl.world;
   static const int unroll = [] {
     const char* e = getenv("B200DDP_NVLS_UNROLL");
@@ -939,11 +1054,11 @@ cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, u
   const int grid = clamp_grid((slice + step - 1) / step, max_ctas, dflt);
   B200_DISPATCH_DT(dtype, {
     if (unroll == 2)
-      nvls_kernel<DT, 2><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec);
+      nvls_kernel<DT, 2><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec, scale);
     else if (unroll == 8)
-      nvls_kernel<DT, 8><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec);
+      nvls_kernel<DT, 8><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec, scale);
     else
-      nvls_kernel<DT, 4><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec);
+      nvls_kernel<DT, 4><<<grid, kArThreads, 0, s>>>(pt, ctl, mc_base, in_off, out_off, nvec, scale);
   });
   return cudaGetLastError();
 }
@@ -1012,8 +1127,12 @@ cudaError_t prepare_ws() {
 template <int DT>
 cudaError_t prepare_dt(int world) {
   cudaError_t e;
-  if ((e = preload(multi_tensor_copy_kernel<DT, false>)) != cudaSuccess) return e;
-  if ((e = preload(multi_tensor_copy_kernel<DT, true>)) != cudaSuccess) return e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, false, 2>)) != cudaSuccess) return e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, true, 2>)) != cudaSuccess) return e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, false, 4>)) != cudaSuccess) return e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, true, 4>)) != cudaSuccess) return e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, false, 8>)) != cudaSuccess) return e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, true, 8>)) != cudaSuccess) return e;
   if ((e = preload(fused_bucket_kernel<DT, 1>)) != cudaSuccess) return e;
   if ((e = preload(nvls_kernel<DT, 2>)) != cudaSuccess) return e;
   if ((e = preload(nvls_kernel<DT, 4>)) != cudaSuccess) return e;

@@ -1,5 +1,5 @@
-// native_reducer.cpp — the Reducer's per-parameter hook loop in C++ (a torch extension, opt-in with
-// B200DDP_NATIVE=1).
+// native_reducer.cpp — the Reducer's per-parameter hook loop in C++ (a torch extension; the default hook loop
+// when it is built, B200DDP_NATIVE=0 selects the Python loop of reducer.py).
 //
 // The reference's DDP runs this loop natively (c10d::Reducer: autograd_hook -> mark_variable_ready ->
 // mark_bucket_ready -> all_reduce_bucket -> finalize_backward, torch:include/torch/csrc/distributed/c10d/
@@ -30,7 +30,7 @@ namespace {
 using fn_stream_wait = int (*)(void*, void*, void*);
 using fn_flatten = int (*)(void*, const void* const*, const uint64_t*, const uint64_t*, int, int, uint64_t, float, void*);
 using fn_unflatten = int (*)(void*, void* const*, const uint64_t*, const uint64_t*, int, int, uint64_t, void*);
-using fn_allreduce = int (*)(void*, uint64_t, uint64_t, uint64_t, int, int, int, void*);
+using fn_allreduce = int (*)(void*, uint64_t, uint64_t, uint64_t, int, int, int, float, void*);
 using fn_fused = int (*)(void*, void* const*, const uint64_t*, const uint64_t*, int, int, uint64_t, uint64_t, float, void*);
 using fn_poll = int (*)(void*);
 using fn_last_error = const char* (*)(void*);
@@ -42,6 +42,9 @@ struct Bucket {
   uint64_t nbytes = 0, arena_off = 0, out_off = 0;
   int algo = 0;
   bool fused = false;
+  // gradient_as_bucket_view (reducer.hpp:238,328-334): views of the bucket in the arena, one per parameter; when
+  // present the bucket is not unflattened, the parameters' .grad are re-pointed at these views instead
+  std::vector<at::Tensor> views;
   // per iteration
   int64_t pending = 0;
   bool ready = false;
@@ -85,9 +88,17 @@ class NativeReducer {
 
   ~NativeReducer() { remove_hooks(); }
 
-  // buckets: list of (param_indices, offsets_el, lengths_el, dtype_code, nbytes, arena_off, out_off, algo, fused)
+  // the engine re-created its context (arena regrow): later launches go to the new one
+  void rebind(uintptr_t ctx) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (armed_) throw std::runtime_error("cannot rebind the context while a backward is in flight");
+    ctx_ = reinterpret_cast<void*>(ctx);
+  }
+
+  // buckets: list of (param_indices, offsets_el, lengths_el, dtype_code, nbytes, arena_off, out_off, algo, fused,
+  //                   views)   — views: [] or one arena view per parameter (gradient_as_bucket_view)
   void configure(const std::vector<std::tuple<std::vector<int64_t>, std::vector<uint64_t>, std::vector<uint64_t>, int64_t,
-                                              uint64_t, uint64_t, uint64_t, int64_t, bool>>& buckets) {
+                                              uint64_t, uint64_t, uint64_t, int64_t, bool, std::vector<at::Tensor>>>& buckets) {
     std::lock_guard<std::mutex> lk(mu_);
     if (armed_) throw std::runtime_error("cannot re-configure buckets while a backward is in flight");
     buckets_.clear();
@@ -98,8 +109,11 @@ class NativeReducer {
           std::make_tuple(std::get<0>(buckets[b]), std::get<1>(buckets[b]), std::get<2>(buckets[b]),
                           static_cast<int>(std::get<3>(buckets[b])), std::get<4>(buckets[b]), std::get<5>(buckets[b]),
                           std::get<6>(buckets[b]), static_cast<int>(std::get<7>(buckets[b])), std::get<8>(buckets[b]));
+      bk.views = std::get<9>(buckets[b]);
       if (bk.params.size() != bk.offs.size() || bk.params.size() != bk.lens.size())
         throw std::runtime_error("bucket tables differ in length");
+      if (!bk.views.empty() && (bk.views.size() != bk.params.size() || bk.fused))
+        throw std::runtime_error("a bucket served as views needs one view per parameter and the three-kernel path");
       for (int64_t p : bk.params) {
         if (p < 0 || p >= static_cast<int64_t>(params_.size()) || param_bucket_[p] != -1)
           throw std::runtime_error("parameter index out of range or assigned to two buckets");
@@ -208,15 +222,30 @@ class NativeReducer {
                     scale_, comm_stream_);
       if (rc) fail("flatten_scale", rc);
       if (world_ > 1) {
-        rc = allreduce_(ctx_, bk.arena_off, bk.out_off, bk.nbytes, bk.dtype, bk.algo, max_ctas_, comm_stream_);
+        rc = allreduce_(ctx_, bk.arena_off, bk.out_off, bk.nbytes, bk.dtype, bk.algo, max_ctas_, 1.0f, comm_stream_);
         if (rc) fail("allreduce", rc);
       }
-      rc = unflatten_(ctx_, ptrs_.data(), bk.offs.data(), bk.lens.data(), static_cast<int>(n), bk.dtype, bk.out_off,
-                      comm_stream_);
-      if (rc) fail("unflatten", rc);
-      launches_ += world_ > 1 ? 3 : 2;
+      if (bk.views.empty()) {
+        rc = unflatten_(ctx_, ptrs_.data(), bk.offs.data(), bk.lens.data(), static_cast<int>(n), bk.dtype, bk.out_off,
+                        comm_stream_);
+        if (rc) fail("unflatten", rc);
+        launches_ += world_ > 1 ? 3 : 2;
+      } else {
+        // no copy back: .grad becomes the view of the reduced bucket; the tensors the flatten kernel still reads
+        // on the side stream stay alive until finalize
+        for (size_t k = 0; k < n; ++k) {
+          at::Tensor& g = params_[bk.params[k]].mutable_grad();
+          if (g.data_ptr() != bk.views[k].data_ptr()) {
+            keepalive_.push_back(g);
+            g = bk.views[k];
+          }
+        }
+        launches_ += world_ > 1 ? 2 : 1;
+      }
     }
-    if (!dense.empty()) {
+    if (!dense.empty() && !bk.views.empty()) {
+      for (auto& t : dense) keepalive_.push_back(std::move(t));  // only read by the flatten kernel
+    } else if (!dense.empty()) {
       // copy the reduced dense stand-ins back on the side stream and keep them alive until finalize
       size_t d = 0;
       if (params_[bk.params[0]].is_cuda()) {
@@ -289,6 +318,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<uintptr_t, const std::map<std::string, uintptr_t>&, int64_t, uintptr_t, int64_t, std::vector<at::Tensor>>(),
            py::arg("ctx"), py::arg("fns"), py::arg("world"), py::arg("comm_stream"), py::arg("max_ctas"), py::arg("params"))
       .def("configure", &NativeReducer::configure)
+      .def("rebind", &NativeReducer::rebind)
       .def("prepare", &NativeReducer::prepare, py::call_guard<py::gil_scoped_release>())
       .def("disarm", &NativeReducer::disarm)
       .def("take_ready_order", &NativeReducer::take_ready_order)

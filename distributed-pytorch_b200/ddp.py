@@ -88,16 +88,24 @@ class DistributedDataParallel(nn.Module):
 
         state = self._module_states()
         if _engine is None:
-            # arena = broadcast staging (construction-time / per-forward sync) + bucket storage
+            # arena = broadcast staging (construction-time / per-forward sync) + bucket storage sized from the
+            # construction-time bucket plan (1x the gradients + the small fused buckets' second slot)
+            import torch.distributed as dist
+
+            world = dist.get_world_size() if dist.is_initialized() else 1
             staging = staging_bytes_for(state)
-            self.engine: BucketEngine = P2PEngine(self.device, arena_bytes_for(params) + staging,
+            self.engine: BucketEngine = P2PEngine(self.device, arena_bytes_for(params, world, cap, first) + staging,
                                                   staging_bytes=staging)
         else:
             self.engine = _engine
+        # B200DDP_GRAD_VIEWS=1 turns torch's own flag on without touching the reference's DDP(model, device_ids=[i])
+        # call (knobs are environment variables so the script signatures stay identical)
+        if os.environ.get("B200DDP_GRAD_VIEWS", "0") not in ("", "0", "false", "no"):
+            gradient_as_bucket_view = True
         if gradient_as_bucket_view:
             # .grad of every parameter in a large bucket becomes a view of the reduced bucket in
-            # the arena (no unflatten pass); as in torch, such gradients must not be detach_()-ed, and the
-            # one-time bucket rebuild is skipped so that live views never change meaning
+            # the arena (no unflatten pass); as in torch, such gradients must not be detach_()-ed.  The one-time
+            # bucket rebuild happens at the next forward; views still alive then are moved to private storage
             self.engine.grad_views = True
         self.gradient_as_bucket_view = bool(gradient_as_bucket_view)
         self._verify_param_shapes(params)
@@ -137,7 +145,17 @@ class DistributedDataParallel(nn.Module):
                                f"between ranks (signatures {sigs})")
 
     # ---- forward -------------------------------------------------------------------------------------
+    def check_health(self, sync: bool = True) -> None:
+        """Raise if a kernel of this rank timed out on a peer (the step's gradients are then NOT the average).
+        The script Trainers call this before writing a checkpoint."""
+        check = getattr(self.engine, "check_health", None)
+        if check is not None:
+            check(sync)
+
     def forward(self, *inputs: Any, **kwargs: Any) -> Any:
+        check = getattr(self.engine, "check_health", None)
+        if check is not None:
+            check(False)  # one host read: a timeout of the previous step surfaces before the next one starts
         if self.device_ids is not None:
             inputs, kwargs = _move(inputs, self.device), _move(kwargs, self.device)
         if self.require_forward_param_sync and self.broadcast_buffers:

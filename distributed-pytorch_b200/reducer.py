@@ -82,6 +82,9 @@ class P2PEngine(BucketEngine):
             raise RuntimeError("b200ddp reduces gradients on B200 GPUs only; module parameters must be on a "
                                f"CUDA device (got {device}) — there is no CPU path")
         self.device = device
+        #: an engine that built its own communicator may replace it with a larger one when a re-bucketing
+        #: needs more arena than the construction-time plan did (tests inject loop-back communicators: fixed)
+        self._owns_comm = comm is None
         self.comm = comm if comm is not None else P2PComm.from_process_group(arena_bytes, device.index)
         self.rank, self.world_size = self.comm.rank, self.comm.world
         # arena = [broadcast staging | buckets]: parameter/buffer broadcasts never touch bucket storage, so a
@@ -118,8 +121,7 @@ class P2PEngine(BucketEngine):
             else:  # two regions for the out-of-place one-shot kernel
                 layout.place(b, out_of_place=multi and b.algo == _lib.ALGO_ONESHOT)
         if layout.total_bytes > self.comm.arena_bytes:
-            raise RuntimeError(f"bucket layout needs {layout.total_bytes} bytes but the arena has "
-                               f"{self.comm.arena_bytes}")
+            self._grow_arena(layout.total_bytes)
         self._tables.clear()
         self._view_cache.clear()
         if multi:
@@ -134,6 +136,29 @@ class P2PEngine(BucketEngine):
                 if b.fused:
                     self.comm.clear(b.arena_off, self.comm.fused_region_bytes(b.nbytes), self._stream_ptr)
             self.comm.barrier(self._stream_ptr)
+
+    def _grow_arena(self, need: int) -> None:
+        """Collective (every rank computes the same layout, so every rank takes this branch together): replace
+        the communicator by one whose arena holds ``need`` bytes.  The arena is sized from the construction-time
+        plan (arena_bytes_for) — 1x the gradients, like torch's bucket storage — and only a re-bucketing that
+        needs more pays this once."""
+        if not self._owns_comm:
+            raise RuntimeError(f"bucket layout needs {need} bytes but the arena has {self.comm.arena_bytes}")
+        import torch.distributed as dist
+
+        torch.cuda.synchronize(self.device)
+        if self.world_size > 1 and dist.is_initialized():
+            dist.barrier()  # no peer still reads the old arena
+        self.comm.destroy()
+        self.comm = P2PComm.from_process_group(need + need // 16 + (2 << 20), self.device.index)
+        self._bcast_plans.clear()
+
+    def owns(self, t: Optional[torch.Tensor]) -> bool:
+        """Is ``t`` a view of this rank's arena (a gradient served as a bucket view)?"""
+        if t is None or not t.is_cuda or self.comm is None:
+            return False
+        lo = self.comm.arena_ptr
+        return lo <= t.data_ptr() < lo + self.comm.arena_bytes
 
     def _table(self, bucket: BucketSpec, tensors: Sequence[torch.Tensor]) -> TensorTable:
         ptrs = [t.data_ptr() for t in tensors]
@@ -193,6 +218,16 @@ class P2PEngine(BucketEngine):
         self._keepalive.clear()
         self.comm.poll_error()
 
+    def check_health(self, sync: bool = False) -> None:
+        """Raise if any kernel of this rank timed out on a peer.  ``sync=True`` first waits for the device (call
+        it before writing a checkpoint: a poisoned step must never be saved); without it this is one host read
+        (called at the start of every forward, so the exception surfaces at most one step late)."""
+        if self.comm is None:
+            return
+        if sync:
+            torch.cuda.synchronize(self.device)
+        self.comm.poll_error()
+
     # ---- control plane (host side, rare) -------------------------------------------------------------
     def sync_order(self, order: List[int]) -> List[int]:
         if self.world_size == 1 or self.comm.uid is None:
@@ -217,7 +252,7 @@ class P2PEngine(BucketEngine):
         """Chunk ``tensors`` into staging-sized multi-tensor tables of raw 4- or 2-byte elements (bit exact
         for any dtype).  Cached per set of storage addresses: the per-forward buffer sync of a model reuses
         the same plan every step."""
-        key = tuple(t.data_ptr() for t in tensors)
+        key = tuple((t.data_ptr(), t.numel(), t.dtype) for t in tensors)
         plan = self._bcast_plans.get(key)
         if plan is not None:
             return plan
@@ -255,8 +290,9 @@ class P2PEngine(BucketEngine):
         return plan
 
     def broadcast_tensors(self, tensors: Sequence[torch.Tensor], root: int = 0) -> None:
-        """Root's tensors -> every rank through the arena's staging region by peer stores; tensors whose byte
-        size is odd (or that are not contiguous) go through torch.distributed."""
+        """Root's tensors -> every rank through the arena's staging region by peer stores.  Tensors whose byte
+        size is odd, or that are not contiguous, are packed into the staging region with a torch copy (as raw
+        bytes / as a dense tensor) and travel through the same broadcast kernel."""
         if self.world_size == 1 or not tensors:
             return
         comm, s = self.comm, self._stream_ptr
@@ -269,12 +305,29 @@ class P2PEngine(BucketEngine):
             comm.broadcast(0, nbytes, root, s, self.max_ctas)
             if self.rank != root:
                 comm.unflatten(table, code, 0, s)
-        comm.stream_wait(cur, s)
         if odd:
-            import torch.distributed as dist
+            with torch.cuda.stream(self.stream):
+                for t in odd:
+                    self._broadcast_packed(t, root)
+        comm.stream_wait(cur, s)
 
-            for t in odd:
-                dist.broadcast(t, src=root)
+    def _broadcast_packed(self, t: torch.Tensor, root: int) -> None:
+        """One tensor of any layout / byte size: root packs it densely into the staging region (chunk by chunk),
+        the broadcast kernel moves the bytes, the other ranks copy them out.  Runs on the side stream."""
+        comm, s = self.comm, self._stream_ptr
+        dense = t if t.is_contiguous() else t.contiguous()
+        raw = dense.reshape(-1).view(torch.uint8)
+        cap = self.staging_bytes
+        for lo in range(0, raw.numel(), cap):
+            n = min(cap, raw.numel() - lo)
+            stage = comm.view(0, n, torch.uint8)
+            if self.rank == root:
+                stage.copy_(raw[lo:lo + n])
+            comm.broadcast(0, (n + 15) // 16 * 16, root, s, self.max_ctas)
+            if self.rank != root:
+                raw[lo:lo + n].copy_(stage)
+        if dense is not t and self.rank != root:
+            t.copy_(dense)
 
     def close(self) -> None:
         if self.comm is not None:
@@ -310,18 +363,23 @@ class Reducer:
         self.buckets: List[BucketSpec] = []
         self._install(list(reversed(indices)))
         self.has_rebuilt = False
+        self._rebuild_pending = False
         self.armed = False
         self.require_sync = True
         self._callback_queued = False
         self._ready_order: List[int] = []
         self._unfinished = False
         self.iterations = 0
-        # opt-in (B200DDP_NATIVE=1): the same state machine in C++ on the autograd thread (csrc/native_reducer.cpp)
+        # The per-parameter hook loop runs in C++ on the autograd thread (csrc/native_reducer.cpp), as torch's own
+        # Reducer does, whenever the extension can be loaded; B200DDP_NATIVE=0 (or an engine other than the
+        # product engine: the CPU host-logic tests) selects the same state machine in Python below.
         self._native = None
+        self._native_ctx = None
         self._hooks = []
-        if _native.wanted() and isinstance(engine, P2PEngine) and not engine.grad_views:
-            mod = _native.build_native()
-            self._native = mod.NativeReducer(engine.comm.ctx_address, engine.comm.function_table(), engine.world_size,
+        mod = _native.load_native() if (_native.wanted() and isinstance(engine, P2PEngine)) else None
+        if mod is not None:
+            self._native_ctx = engine.comm.ctx_address
+            self._native = mod.NativeReducer(self._native_ctx, engine.comm.function_table(), engine.world_size,
                                              engine._stream_ptr, engine.max_ctas, self.params)
             self._native.configure(self._native_buckets())
         else:
@@ -341,6 +399,9 @@ class Reducer:
             for i in b.param_indices:
                 self._param_bucket[i] = b.index
         if getattr(self, "_native", None) is not None:
+            if self.engine.comm.ctx_address != self._native_ctx:  # the engine regrew its arena
+                self._native_ctx = self.engine.comm.ctx_address
+                self._native.rebind(self._native_ctx)
             self._native.configure(self._native_buckets())
         self._pending = [0] * len(specs)
         self._bucket_ready = [False] * len(specs)
@@ -348,8 +409,15 @@ class Reducer:
         self._next_bucket = 0
 
     def _native_buckets(self):
-        return [(b.param_indices, b.offsets_el, b.lengths_el, b.dtype_code, b.nbytes, b.arena_off, b.out_off, b.algo,
-                 b.fused) for b in self.buckets]
+        eng = self.engine
+        out = []
+        for b in self.buckets:
+            views = []
+            if eng.grad_views and not b.fused:
+                views = eng._bucket_views(b, [self.params[i] for i in b.param_indices])
+            out.append((b.param_indices, b.offsets_el, b.lengths_el, b.dtype_code, b.nbytes, b.arena_off, b.out_off,
+                        b.algo, b.fused, views))
+        return out
 
     def disarm(self) -> None:
         """The coming backward must not reduce (no_sync, or a forward without grad)."""
@@ -375,6 +443,9 @@ class Reducer:
             else:
                 self._native.disarm()
             return
+        if self._rebuild_pending:
+            self._rebuild_pending = False
+            self._rebuild_buckets()
         if self._unfinished:
             raise RuntimeError(
                 "Expected to have finished reduction in the prior iteration before starting a new one. "
@@ -435,13 +506,9 @@ class Reducer:
         self._unfinished = False
         self.iterations += 1
         if not self.has_rebuilt:
-            if getattr(self.engine, "grad_views", False):
-                # with gradient_as_bucket_view the live .grad tensors are views of the CURRENT layout (the
-                # optimizer reads them right after this callback): the layout is never changed under them
-                self.has_rebuilt = True
-                self._ready_order = []
-            else:
-                self._rebuild_buckets()
+            # the one-time rebuild happens at the next forward (as torch drives it, distributed.py:1584): with
+            # gradient_as_bucket_view the optimizer still reads .grad views of the CURRENT layout after this callback
+            self._rebuild_pending = True
 
     def _rebuild_buckets(self) -> None:
         """One-time re-bucketing in gradient-ready order (rank 0's order wins on every rank)."""
@@ -450,6 +517,13 @@ class Reducer:
         self.has_rebuilt = True
         if sorted(order) != list(range(len(self.params))):
             return  # incomplete order (should not happen once finalize succeeded): keep current buckets
+        owns = getattr(self.engine, "owns", None)
+        if owns is not None and getattr(self.engine, "grad_views", False):
+            # gradients still alive as views of the OLD layout (no zero_grad since the last step: gradient
+            # accumulation) move to private storage before the arena is laid out anew
+            for p in self.params:
+                if owns(p.grad):
+                    p.grad = p.grad.clone()
         sizes = [self._sizes[i] for i in order]
         keys = [self._keys[i] for i in order]
         indices, _ = compute_bucket_assignment_by_size(
@@ -465,12 +539,34 @@ class Reducer:
             self._native = None
 
 
-def arena_bytes_for(params: Sequence[torch.nn.Parameter]) -> int:
-    """Bucket storage that fits any bucketing of ``params``: two regions per bucket plus region alignment;
-    tiny buckets on the LL path take 4*ws (<= 32) times their <= 32 KiB size, bounded per parameter."""
-    payload = sum((p.numel() * p.element_size() + 15) // 16 * 16 for p in params)
-    ll_extra = sum(32 * min((p.numel() * p.element_size() + 15) // 16 * 16, 32 << 10) for p in params)
-    return 2 * (payload + len(params) * BucketLayout.REGION_ALIGN) + ll_extra + (1 << 20)
+def arena_bytes_for(params: Sequence[torch.nn.Parameter], world_size: int = 1,
+                    bucket_bytes_cap: int = DEFAULT_BUCKET_BYTES_CAP,
+                    first_bucket_bytes_cap: int = DEFAULT_FIRST_BUCKET_BYTES) -> int:
+    """Bucket storage for the CONSTRUCTION-TIME plan of ``params`` (the same bucketing and region rules
+    ``Reducer`` / ``P2PEngine.plan`` apply), plus 1/16 + 2 MiB of slack for the one-time re-bucketing: 1x the
+    gradients for in-place buckets (like torch's bucket storage), two slots only for buckets on the fused
+    single-launch path (<= 256 KiB) and the LL slot sets only for buckets <= 32 KiB.  A re-bucketing that needs
+    more makes the engine replace its arena once (P2PEngine._grow_arena)."""
+    lib = _lib.load()
+    fused_max = min(int(lib.b200ddp_fused_max_bytes()), int(os.environ.get("B200DDP_FUSED_MAX", str(1 << 30))))
+    max_table = int(lib.b200ddp_max_table_tensors())
+    out_of_place = os.environ.get("B200DDP_ALGO", "") == str(_lib.ALGO_ONESHOT) or \
+        int(os.environ.get("B200DDP_ONESHOT_MAX", "0") or 0) > 0
+    params = list(params)
+    sizes = [p.numel() * p.element_size() for p in params]
+    keys = [(p.dtype, p.device) for p in params]
+    indices, _ = compute_bucket_assignment_by_size(sizes, keys, [int(first_bucket_bytes_cap), int(bucket_bytes_cap)])
+    align = BucketLayout.REGION_ALIGN
+    total = 0
+    for idxs in indices:
+        es = params[idxs[0]].element_size()
+        nbytes = max(16, sum((params[i].numel() * es + 15) // 16 * 16 for i in idxs))
+        if nbytes <= fused_max and len(idxs) <= max_table:
+            region = max(nbytes, int(lib.b200ddp_fused_region_bytes_for(int(world_size), nbytes)))
+        else:
+            region = (nbytes + align - 1) // align * align * (2 if (out_of_place and world_size > 1) else 1)
+        total += (region + align - 1) // align * align
+    return total + total // 16 + (2 << 20)
 
 
 def staging_bytes_for(tensors: Sequence[torch.Tensor]) -> int:

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define B200DDP_ABI_VERSION 1
+#define B200DDP_ABI_VERSION 2
 
 /* maximum ranks of one NVSwitch domain this library addresses (one 8-GPU box, north_star) */
 #define B200DDP_MAX_WORLD 8
@@ -122,14 +122,18 @@ int b200ddp_unflatten(b200ddp_ctx* ctx, void* const* grad_ptrs, const uint64_t* 
                       const uint64_t* len_el, int n, int dtype, uint64_t bucket_off, void* stream);
 
 /* SUM-allreduce `nbytes` (multiple of 16) of arena[in_off] over all ranks into arena[out_off] on every
- * rank (in_off == out_off allowed except for ONESHOT), accumulating in fp32.  Replaces
+ * rank (in_off == out_off allowed except for ONESHOT), accumulating in fp32; the reduced sum is multiplied by
+ * `scale` (fp32, one rounding; 1.0 = none) before it is written back.  The Reducer passes 1.0 because it
+ * pre-scales in flatten_scale exactly like the reference (reducer.hpp:276 divides before the allreduce); the
+ * comm-hook shim passes 1/world, since torch hands a hook an UNdivided bucket
+ * (torch:nn/parallel/distributed.py:2021-2023).  Replaces
  * Reducer::all_reduce_bucket -> _AllReduceBySumCommHook -> ProcessGroupNCCL::allreduce -> ncclAllReduce
  * (reducer.hpp:524, default_comm_hooks.hpp:41-51, ProcessGroupNCCL.hpp:856).  The kernel itself issues
  * the NVLink traffic (peer loads/stores, or multimem for NVLS); `max_ctas` caps the grid (0 = library
  * default) so the backward's GEMMs keep the remaining SMs.  With world == 1 this is a no-op copy when
  * in_off != out_off. */
 int b200ddp_allreduce(b200ddp_ctx* ctx, uint64_t in_off, uint64_t out_off, uint64_t nbytes, int dtype,
-                      int algo, int max_ctas, void* stream);
+                      int algo, int max_ctas, float scale, void* stream);
 
 /* Small-bucket fast path: flatten+scale, one-shot allreduce and unflatten of one bucket in ONE launch
  * (n <= b200ddp_max_table_tensors(), bucket bytes <= b200ddp_fused_max_bytes()).  Equivalent to
@@ -144,6 +148,15 @@ int b200ddp_fused_bucket(b200ddp_ctx* ctx, void* const* grad_ptrs, const uint64_
 int b200ddp_max_table_tensors(void);
 uint64_t b200ddp_fused_max_bytes(void);
 uint64_t b200ddp_fused_region_bytes(b200ddp_ctx* ctx, uint64_t bucket_bytes);
+/* the same for a world size given explicitly (no context: callers size the arena BEFORE b200ddp_init) */
+uint64_t b200ddp_fused_region_bytes_for(int world, uint64_t bucket_bytes);
+
+/* Diagnostic: arena[dst_off] of this rank <- arena[src_off] of rank `peer`, `nbytes` (multiple of 16) pulled
+ * with 16-byte loads over the peer mapping.  No synchronisation with the peer: it measures the per-direction
+ * NVLink read bandwidth a kernel can reach on this box (the denominator bench.py reports as
+ * `nvlink_peak_measured`); `peer` == own rank measures the local HBM copy. */
+int b200ddp_peer_read(b200ddp_ctx* ctx, int peer, uint64_t src_off, uint64_t dst_off, uint64_t nbytes,
+                      int max_ctas, void* stream);
 
 /* Zero arena[off, off + nbytes) on `stream` (offset and size multiples of 16). */
 int b200ddp_clear(b200ddp_ctx* ctx, uint64_t off, uint64_t nbytes, void* stream);
@@ -164,7 +177,9 @@ int b200ddp_stream_wait(b200ddp_ctx* ctx, void* waiter, void* signaled);
 /* ---- diagnostics --------------------------------------------------------------------------------- */
 
 /* Returns 0, or B200DDP_ETIMEOUT if any kernel since the last poll observed a peer timeout (the flag
- * lives in mapped host memory; polling does not synchronise the device). */
+ * lives in mapped host memory; polling does not synchronise the device).  A timeout is sticky on the device
+ * side: the rank's later collective kernels return at once and unflatten launches leave the gradients
+ * untouched, so a half-reduced bucket is never scattered; the context must be destroyed afterwards. */
 int b200ddp_poll_error(b200ddp_ctx* ctx);
 /* In-kernel barrier timeout in milliseconds (default 600000 = 10 minutes, the order of NCCL's watchdog: a peer
  * may legitimately arrive late, e.g. while rank 0 writes a checkpoint). */

@@ -1,4 +1,4 @@
-"""The opt-in C++ hook loop (csrc/native_reducer.cpp) exercised on CPU: its C-ABI calls are pointed at recording
+"""The C++ hook loop (csrc/native_reducer.cpp, the default on the product engine) exercised on CPU: its C-ABI calls are pointed at recording
 ctypes callbacks, so the state machine — post hooks on the AccumulateGrad nodes, pending counts, strict
 bucket order, engine-callback finalize, ready-order capture, error paths — is checked without a GPU."""
 import ctypes as C
@@ -37,7 +37,7 @@ class FakeAbi:
             "b200ddp_stream_wait": C.CFUNCTYPE(i, vp, vp, vp)(rec("stream_wait")),
             "b200ddp_flatten_scale": C.CFUNCTYPE(i, vp, pp, pu, pu, i, i, u64, f, vp)(rec("flatten", 4, 6, 7)),
             "b200ddp_unflatten": C.CFUNCTYPE(i, vp, pp, pu, pu, i, i, u64, vp)(rec("unflatten", 4, 6)),
-            "b200ddp_allreduce": C.CFUNCTYPE(i, vp, u64, u64, u64, i, i, i, vp)(rec("allreduce", 1, 2, 3, 5)),
+            "b200ddp_allreduce": C.CFUNCTYPE(i, vp, u64, u64, u64, i, i, i, f, vp)(rec("allreduce", 1, 2, 3, 5, 7)),
             "b200ddp_fused_bucket": C.CFUNCTYPE(i, vp, pp, pu, pu, i, i, u64, u64, f, vp)(rec("fused", 4, 6, 7)),
             "b200ddp_poll_error": C.CFUNCTYPE(i, vp)(rec("poll")),
             "b200ddp_last_error": C.CFUNCTYPE(C.c_char_p, vp)(lambda ctx: b"injected failure"),
@@ -50,10 +50,11 @@ def _model():
     return nn.Sequential(nn.Linear(6, 8), nn.ReLU(), nn.Linear(8, 8), nn.ReLU(), nn.Linear(8, 2))
 
 
-def _buckets(groups, fused=False, algo=2):
+def _buckets(groups, fused=False, algo=2, views=None):
     out, off = [], 0
-    for g in groups:
-        out.append((g, [16 * k for k in range(len(g))], [4] * len(g), 0, 64 * len(g), off, off, algo, fused))
+    for bi, g in enumerate(groups):
+        out.append((g, [16 * k for k in range(len(g))], [4] * len(g), 0, 64 * len(g), off, off, algo, fused,
+                    [] if views is None else views[bi]))
         off += 4096
     return out
 
@@ -79,6 +80,7 @@ def test_hooks_launch_buckets_in_index_order_and_finalize(native):
     assert all(abs(c[3] - 0.5) < 1e-7 for c in flat)  # 1/world pre-scale
     ar = [c for c in abi.calls if c[0] == "allreduce"]
     assert [(c[1], c[2], c[3], c[4]) for c in ar] == [(0, 0, 128, 2), (4096, 4096, 128, 2), (8192, 8192, 128, 2)]
+    assert all(c[5] == 1.0 for c in ar)  # the Reducer pre-scales in flatten; the allreduce itself does not scale
     assert red.take_ready_order() == [5, 4, 3, 2, 1, 0]  # gradient-ready order of a chain
     assert red.take_ready_order() == []
 
@@ -144,6 +146,33 @@ def test_errors_surface_as_python_exceptions(native):
         p(torch.randn(2, 3)).sum().backward()
     with pytest.raises(RuntimeError, match="finished reduction in the prior iteration"):
         red2.prepare()
+
+
+def test_bucket_views_replace_unflatten_and_become_the_grads(native):
+    """gradient_as_bucket_view: no unflatten call; .grad of every parameter is re-pointed at the view handed to
+    configure(); a second iteration whose gradients ARE the views flattens in place (same pointers)."""
+    abi = FakeAbi()
+    m = _model()
+    params = list(m.parameters())
+    groups = [[4, 5], [2, 3], [0, 1]]
+    views = [[torch.zeros_like(params[i]) for i in g] for g in groups]
+    red = native.NativeReducer(1, abi.table, 2, 0, 0, params)
+    red.configure(_buckets(groups, views=views))
+    red.prepare()
+    m(torch.randn(2, 6)).sum().backward()
+    assert [c[0] for c in abi.calls] == ["stream_wait", "flatten", "allreduce"] * 3 + ["stream_wait", "poll"]
+    assert red.launches() == 6
+    for g, vs in zip(groups, views):
+        for i, v in zip(g, vs):
+            assert params[i].grad.data_ptr() == v.data_ptr()
+    red.rebind(4321)  # a regrown arena: allowed between iterations
+    red.prepare()
+    m(torch.randn(2, 6)).sum().backward()  # accumulates into the views in place
+    for g, vs in zip(groups, views):
+        for i, v in zip(g, vs):
+            assert params[i].grad.data_ptr() == v.data_ptr()
+    with pytest.raises(RuntimeError, match="one view per parameter"):
+        red.configure(_buckets(groups, fused=True, views=views))
 
 
 def test_hooks_are_removed_with_the_reducer(native):

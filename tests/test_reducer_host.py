@@ -34,10 +34,16 @@ def test_initial_buckets_follow_reverse_definition_order_and_rebuild_once():
     # launches happened strictly in bucket-index order and covered every bucket
     assert eng.launched == list(range(len(sizes0)))
     assert eng.finalized == 1
-    # one rebuild after iteration 0, in gradient-ready order (reverse of definition for a chain)
+    # one rebuild after iteration 0, in gradient-ready order (reverse of definition for a chain); like torch it
+    # is carried out by the NEXT forward (distributed.py:1584), so that gradients served as bucket views stay
+    # valid for the optimizer step in between
+    assert len(eng.plans) == 1 and not ddp.reducer.has_rebuilt
+    eng.launched.clear()
+    _step(ddp)
     assert len(eng.plans) == 2 and ddp.reducer.has_rebuilt
     ready = [i for b in eng.plans[1] for i in b.param_indices]
     assert ready == [5, 4, 3, 2, 1, 0]
+    assert eng.launched == list(range(len(eng.plans[1])))
     eng.launched.clear()
     _step(ddp)
     assert eng.launched == list(range(len(eng.plans[1])))
