@@ -4,14 +4,27 @@ One optimisation step is the reference's ``_run_batch`` (ref:multigpu.py:38-43):
 -> loss -> backward -> step.  The gradient allreduce fires inside ``loss.backward()`` through the hooks
 ``b200ddp.DistributedDataParallel`` installed — nothing here knows about it, exactly as in the reference.
 
-Opt-in extension (not in the reference): ``enable_cuda_graph`` captures that same step — including the
-bucket kernels our Reducer enqueues on its side stream — into one CUDA graph, so a launch-bound step (the
-toy model's ~15 tiny kernels) is replayed with a single launch.  This works because the allreduce kernels
-keep their barrier generation in device memory (no per-launch host state, see csrc/kernels.cu).
+What this module adds around that step (none of it changes what a step computes):
+
+* **CUDA-graph replay of the step** — once the step has run ``GRAPH_AFTER`` times eagerly on batches of one
+  shape, it is captured (forward, loss, backward with the bucket kernels our Reducer enqueues on its side stream,
+  optimizer step) and later batches of that shape replay it with one launch.  This is the default of the script
+  Trainers (``B200DDP_GRAPH=auto``); ``B200DDP_GRAPH=0`` keeps every step eager, ``=1`` captures on the first
+  call.  A batch of another shape (the last, partial batch of a shard) runs eagerly; a model that cannot be
+  captured (data-dependent control flow, a non-capturable optimizer) falls back to eager for good.  Capture works
+  because the allreduce kernels keep their barrier generation in device memory (csrc/kernels.cu).
+* **a pipelined host path** — batches that arrive as HOST tensors (the reference's ``DataLoader(pin_memory=True)``,
+  ref:multigpu.py:72-79) go through two alternating graphs that START with the host->device copy of their own
+  pinned staging buffer and END with the device->host copy of the loss: batch i+1 is staged while step i runs, the
+  loss of step i is read when step i+1 has been queued (``PendingLoss``).
+* **a device-resident shard**  — ``B200DDP_RESIDENT=1``: the rank's ``DistributedSampler`` shard of
+  ``MyTrainDataset`` is moved to HBM once and the captured step gathers its batch by a device-side cursor, so a
+  step is exactly one graph launch and no per-batch ``source.to(gpu_id)`` (ref:multigpu.py:48-50).
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+import os
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 from torch.utils.data import DataLoader, Dataset
@@ -34,28 +47,101 @@ def sharded_loader(dataset: Dataset, batch_size: int) -> DataLoader:
                       pin_memory=True)
 
 
+def _truthy(value: Optional[str]) -> bool:
+    return value is not None and value.lower() not in ("", "0", "false", "no", "off")
+
+
+class PendingLoss:
+    """The loss of a replayed step whose device->host copy is part of the replay: reading it waits for that step
+    only (an event recorded right after the replay), not for the device."""
+
+    __slots__ = ("_host", "_event")
+
+    def __init__(self, host: torch.Tensor, event: torch.cuda.Event) -> None:
+        self._host, self._event = host, event
+
+    def item(self) -> float:
+        self._event.synchronize()
+        return float(self._host)
+
+    __float__ = item
+
+
+class _Slot:
+    """One captured step together with the static buffers it reads and writes."""
+
+    __slots__ = ("graph", "source", "targets", "loss", "host_pack", "dev_pack", "host_source", "host_targets",
+                 "host_loss", "done")
+
+    def __init__(self) -> None:
+        self.graph = None
+        self.done = None
+
+
+def _signature(source: torch.Tensor, targets: torch.Tensor):
+    return (tuple(source.shape), source.dtype, tuple(targets.shape), targets.dtype)
+
+
 class TrainerCore:
     #: loss used by ``_run_batch``.  The reference's choice (ref:multigpu.py:41) — note SURVEY §9 Q1: with
     #: the toy Linear(20,1) head this loss, and therefore every gradient, is identically zero.
     loss_fn: Callable = staticmethod(torch.nn.CrossEntropyLoss())
+
+    #: eager steps of one batch shape before the step is captured in ``auto`` mode (they are real training steps;
+    #: they also carry the Reducer's one-time bucket rebuild, which must precede capture)
+    GRAPH_AFTER = 3
 
     model: torch.nn.Module
     optimizer: torch.optim.Optimizer
     train_data: DataLoader
     gpu_id: int
 
-    _graph: Optional[torch.cuda.CUDAGraph] = None
-    _g_source: Optional[torch.Tensor] = None
-    _g_targets: Optional[torch.Tensor] = None
-    _g_loss: Optional[torch.Tensor] = None
     graph_kernel_launches: int = 0  # b200ddp kernels captured per replayed step
 
+    # ---- construction --------------------------------------------------------------------------------
     def _adopt(self, wrapped: torch.nn.Module, train_data, optimizer: torch.optim.Optimizer, gpu_id: int,
                save_every: int) -> None:
         """Common constructor tail of the script Trainers."""
         self.gpu_id, self.save_every = gpu_id, save_every
         self.train_data, self.optimizer = train_data, optimizer
         self.model = wrapped
+
+    def _state(self) -> Dict:
+        st = self.__dict__.get("_graph_state")
+        if st is None:
+            st = self.__dict__["_graph_state"] = {
+                "mode": os.environ.get("B200DDP_GRAPH", "auto").lower(), "sig": None, "eager_run": 0,
+                "slots": {}, "failed": None, "host_step": 0, "resident": None}
+            if st["mode"] in ("1", "on", "true", "yes"):
+                st["mode"] = "on"
+            elif st["mode"] in ("0", "off", "false", "no"):
+                st["mode"] = "off"
+            elif st["mode"] != "auto":
+                raise ValueError(f"B200DDP_GRAPH must be auto, 0 or 1 (got {st['mode']!r})")
+        return st
+
+    @property
+    def _graph(self):
+        """The captured step for device-resident batches, if any (kept for callers of round 1's API)."""
+        slot = self._state()["slots"].get("dev")
+        return None if slot is None else slot.graph
+
+    @_graph.setter
+    def _graph(self, value) -> None:
+        st = self._state()
+        if value is None:  # drop every captured step: the next calls run eagerly (and may re-capture)
+            st["slots"].clear()
+            st["sig"], st["eager_run"], st["mode"] = None, 0, "off"
+        else:
+            slot = st["slots"].setdefault("dev", _Slot())
+            slot.graph = value
+
+    # ---- the step ------------------------------------------------------------------------------------
+    def _device(self) -> torch.device:
+        gpu = getattr(self, "gpu_id", None)
+        if gpu is None:
+            return next(self.model.parameters()).device
+        return torch.device("cuda", gpu) if isinstance(gpu, int) else torch.device(gpu)
 
     def _eager_step(self, source: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         self.optimizer.zero_grad()
@@ -64,48 +150,236 @@ class TrainerCore:
         self.optimizer.step()
         return loss.detach()
 
-    def _run_batch(self, source: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        if self._graph is None:
-            return self._eager_step(source, targets)
-        self._g_source.copy_(source, non_blocking=True)
-        self._g_targets.copy_(targets, non_blocking=True)
-        self._graph.replay()
-        return self._g_loss
+    def _eager_any(self, source: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        if not source.is_cuda:  # ref:multigpu.py:48-50
+            dev = self._device()
+            source, targets = source.to(dev, non_blocking=True), targets.to(dev, non_blocking=True)
+        return self._eager_step(source, targets)
 
-    def enable_cuda_graph(self, source: torch.Tensor, targets: torch.Tensor, warmup: int = 3) -> None:
-        """Capture one full step on batches shaped like (source, targets); later ``_run_batch`` calls copy
-        their batch into the captured input buffers and replay.  The ``warmup`` eager steps are real
-        training steps (they also trigger the Reducer's one-time bucket rebuild before capture).  All
-        ranks must call this collectively: the captured allreduce kernels synchronise across ranks."""
-        if self._graph is not None:
-            return
-        dev = source.device
-        self._g_source, self._g_targets = source.clone(), targets.clone()
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(max(2, warmup)):
-                self._eager_step(self._g_source, self._g_targets)
-        torch.cuda.current_stream(dev).wait_stream(side)
+    def _run_batch(self, source: torch.Tensor, targets: torch.Tensor):
+        """One optimisation step on ``(source, targets)`` — device tensors as in the reference, or the loader's
+        host tensors.  Returns the loss (a 0-dim tensor, or a ``PendingLoss`` on the pipelined host path)."""
+        st = self._state()
+        if st["mode"] == "off" or st["failed"] is not None:
+            return self._eager_any(source, targets)
+        sig = _signature(source, targets)
+        if st["sig"] != sig:
+            if st["slots"]:
+                # a batch shaped unlike the captured one (the partial batch that ends a shard): eager this once
+                return self._eager_any(source, targets)
+            st["sig"], st["eager_run"] = sig, 0
+        kind = "dev" if source.is_cuda else "host"
+        if kind not in st["slots"]:
+            # eager steps first: GRAPH_AFTER of them in auto mode, and never fewer than two (the Reducer's one-time
+            # bucket rebuild happens at the second forward and must precede capture)
+            if st["eager_run"] < (self.GRAPH_AFTER if st["mode"] == "auto" else 2):
+                st["eager_run"] += 1
+                return self._eager_any(source, targets)
+            if not self._try_capture(kind, source, targets):
+                return self._eager_any(source, targets)
+        if kind == "dev":
+            slot = st["slots"]["dev"]
+            slot.source.copy_(source, non_blocking=True)
+            slot.targets.copy_(targets, non_blocking=True)
+            slot.graph.replay()
+            return slot.loss
+        slots = st["slots"]["host"]
+        slot = slots[st["host_step"] & 1]
+        st["host_step"] += 1
+        slot.done.synchronize()  # the replay that last read this staging buffer (two steps ago) has finished
+        slot.host_source.copy_(source)
+        slot.host_targets.copy_(targets)
+        slot.graph.replay()
+        slot.done.record()
+        return PendingLoss(slot.host_loss, slot.done)
+
+    # ---- capture -------------------------------------------------------------------------------------
+    def _capture_step(self, prologue: Callable[[], Tuple[torch.Tensor, torch.Tensor]],
+                      epilogue: Optional[Callable[[torch.Tensor], None]] = None):
+        """Capture prologue -> forward -> loss -> backward (with our bucket kernels) -> optimizer step -> epilogue.
+        All ranks must call this collectively: the captured allreduce kernels synchronise across ranks."""
+        dev = self._device()
         torch.cuda.synchronize(dev)
         comm = getattr(getattr(self.model, "engine", None), "comm", None)
         n0 = comm.launch_count if comm is not None else 0
         self.optimizer.zero_grad(set_to_none=True)  # gradients are (re)created inside the graph's pool
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            loss = self.loss_fn(self.model(self._g_source), self._g_targets)
+            source, targets = prologue()
+            loss = self.loss_fn(self.model(source), targets)
             loss.backward()
             self.optimizer.step()
-            self._g_loss = loss.detach()
+            out = loss.detach()
+            if epilogue is not None:
+                epilogue(out)
         self.graph_kernel_launches = (comm.launch_count - n0) if comm is not None else 0
-        self._graph = graph
+        return graph, out
 
+    def _try_capture(self, kind: str, source: torch.Tensor, targets: torch.Tensor) -> bool:
+        st = self._state()
+        try:
+            if kind == "dev":
+                st["slots"]["dev"] = self._capture_dev(source, targets)
+            else:
+                st["slots"]["host"] = [self._capture_host(source, targets) for _ in range(2)]
+            if _truthy(os.environ.get("B200DDP_VERBOSE")):
+                print(f"[GPU{getattr(self, 'gpu_id', '?')}] training step captured into a CUDA graph (kind={kind}, "
+                      f"b200ddp kernels per replay={self.graph_kernel_launches})", flush=True)
+            return True
+        except Exception as exc:  # the model / optimizer cannot be captured: this Trainer stays eager
+            st["failed"] = exc
+            st["slots"].pop(kind, None)
+            reducer = getattr(self.model, "reducer", None)
+            if reducer is not None and hasattr(reducer, "abort_iteration"):
+                reducer.abort_iteration()
+            try:
+                torch.cuda.synchronize(self._device())
+            except Exception:
+                pass
+            if _truthy(os.environ.get("B200DDP_GRAPH_STRICT")):
+                raise
+            print(f"[GPU{getattr(self, 'gpu_id', '?')}] CUDA-graph capture of the training step failed "
+                  f"({type(exc).__name__}: {exc}); continuing eagerly")
+            return False
+
+    def _capture_dev(self, source: torch.Tensor, targets: torch.Tensor) -> _Slot:
+        slot = _Slot()
+        slot.source, slot.targets = source.clone(), targets.clone()
+        slot.graph, slot.loss = self._capture_step(lambda: (slot.source, slot.targets))
+        return slot
+
+    def _capture_host(self, source: torch.Tensor, targets: torch.Tensor) -> _Slot:
+        """A step that begins with the H2D copy of its own pinned staging buffer (source and targets packed into
+        one transfer) and ends with the D2H copy of the loss."""
+        dev = self._device()
+        slot = _Slot()
+        sb = source.numel() * source.element_size()
+        tb = targets.numel() * targets.element_size()
+        t_off = (sb + 255) // 256 * 256
+        slot.host_pack = torch.empty(t_off + max(tb, 1), dtype=torch.uint8).pin_memory()
+        slot.dev_pack = torch.empty(t_off + max(tb, 1), dtype=torch.uint8, device=dev)
+        slot.host_source = slot.host_pack[:sb].view(source.dtype).view(source.shape)
+        slot.host_targets = slot.host_pack[t_off:t_off + tb].view(targets.dtype).view(targets.shape)
+        slot.source = slot.dev_pack[:sb].view(source.dtype).view(source.shape)
+        slot.targets = slot.dev_pack[t_off:t_off + tb].view(targets.dtype).view(targets.shape)
+        slot.host_source.copy_(source)
+        slot.host_targets.copy_(targets)
+        slot.host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+        slot.done = torch.cuda.Event()
+
+        def prologue():
+            slot.dev_pack.copy_(slot.host_pack, non_blocking=True)
+            return slot.source, slot.targets
+
+        def epilogue(loss: torch.Tensor) -> None:
+            slot.host_loss.copy_(loss.float(), non_blocking=True)
+
+        slot.graph, slot.loss = self._capture_step(prologue, epilogue)
+        slot.done.record()
+        return slot
+
+    def enable_cuda_graph(self, source: torch.Tensor, targets: torch.Tensor, warmup: int = 3) -> None:
+        """Capture the step NOW for batches shaped like (source, targets) (device tensors).  The ``warmup`` eager
+        steps on that batch are real training steps (at least two run unless the Trainer has already stepped:
+        they carry the Reducer's one-time bucket rebuild).  Collective across ranks."""
+        st = self._state()
+        if "dev" in st["slots"]:
+            return
+        dev = source.device
+        src, tgt = source.clone(), targets.clone()
+        need = max(2, warmup) if st["eager_run"] < 2 else warmup
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(need):
+                self._eager_step(src, tgt)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        st["mode"] = "on" if st["mode"] == "off" else st["mode"]
+        st["failed"] = None
+        st["sig"] = _signature(source, targets)
+        st["slots"]["dev"] = self._capture_dev(source, targets)
+
+    # ---- device-resident shard (SURVEY §8 f.3) -----------------------------------------------------------
+    def enable_resident_shard(self, loader=None) -> bool:
+        """Keep this rank's sampler shard in HBM (``utils.DeviceShardLoader``) and capture a step that gathers
+        its batch from it by a device-side cursor.  ``loader``: a ``DeviceShardLoader``, or None to build one from
+        ``self.train_data`` (a ``DataLoader`` over a ``MyTrainDataset`` with a ``DistributedSampler``).  Returns
+        False (and changes nothing) when the data cannot be made resident.  Collective across ranks."""
+        from .utils import DeviceShardLoader
+
+        st = self._state()
+        if st["resident"] is not None:
+            return True
+        if loader is None:
+            data = self.train_data
+            ds = getattr(data, "dataset", None)
+            if ds is None or not hasattr(ds, "device_shard") or data.batch_size is None:
+                return False
+            loader = DeviceShardLoader(ds, data.batch_size, self._device(), sampler=getattr(data, "sampler", None))
+        bsz = loader.batch_size
+        rows = loader.x.shape[0]
+        full = rows // bsz * bsz
+        if full == 0:
+            return False
+        dev = loader.x.device
+        if st["eager_run"] < 2:  # the Reducer's one-time rebuild must precede capture
+            for _ in range(2):
+                self._eager_step(loader.x[:bsz], loader.y[:bsz])
+            st["eager_run"] += 2
+        res = {"loader": loader, "bsz": bsz, "full": full, "steps": full // bsz,
+               "cursor": torch.zeros((), dtype=torch.int64, device=dev),
+               "lane": torch.arange(bsz, dtype=torch.int64, device=dev)}
+
+        def prologue():
+            idx = res["lane"] + res["cursor"]
+            return loader.x.index_select(0, idx), loader.y.index_select(0, idx)
+
+        def epilogue(_loss: torch.Tensor) -> None:
+            res["cursor"].add_(bsz).remainder_(full)
+
+        try:
+            res["graph"], res["loss"] = self._capture_step(prologue, epilogue)
+        except Exception as exc:
+            st["failed"] = exc
+            reducer = getattr(self.model, "reducer", None)
+            if reducer is not None and hasattr(reducer, "abort_iteration"):
+                reducer.abort_iteration()
+            return False
+        res["cursor"].zero_()
+        st["resident"] = res
+        return True
+
+    def _run_resident_step(self) -> torch.Tensor:
+        """One step on the next resident batch: a single graph launch."""
+        res = self._state()["resident"]
+        res["graph"].replay()
+        return res["loss"]
+
+    def _run_resident_epoch(self) -> None:
+        res = self._state()["resident"]
+        res["cursor"].zero_()
+        for _ in range(res["steps"]):
+            res["graph"].replay()
+        loader = res["loader"]
+        if loader.x.shape[0] > res["full"]:  # the partial batch that ends the shard (the loader keeps it)
+            self._eager_step(loader.x[res["full"]:], loader.y[res["full"]:])
+
+    # ---- epoch loop ------------------------------------------------------------------------------------
     def _run_epoch(self, epoch: int) -> None:
         steps = len(self.train_data)
         first = next(iter(self.train_data))[0]
         print(f"[GPU{self.gpu_id}] Epoch {epoch} | Batchsize: {len(first)} | Steps: {steps}")
+        st = self._state()
+        if _truthy(os.environ.get("B200DDP_RESIDENT")) and st["mode"] != "off" and self.enable_resident_shard():
+            self._run_resident_epoch()
+            return
         for source, targets in self.train_data:
-            if self._graph is not None:  # the replayed step copies host batches straight into its input buffers
-                self._run_batch(source, targets)
-            else:
-                self._run_batch(source.to(self.gpu_id), targets.to(self.gpu_id))
+            # host batches go in as they come: the eager path moves them (ref:multigpu.py:48-50), the replayed
+            # path stages them itself
+            self._run_batch(source, targets)
+
+    def _check_health(self) -> None:
+        """Before a checkpoint: wait for the device and raise if any bucket kernel timed out on a peer."""
+        check = getattr(self.model, "check_health", None)
+        if check is not None:
+            check(True)

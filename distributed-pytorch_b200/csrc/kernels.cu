@@ -954,12 +954,9 @@ namespace {
 // Vectors per thread and tile of the copy kernel (B200DDP_COPY_UNROLL = 2 | 4 | 8 forces one).  Measured on B200
 // (tools/ab_copy.py, profiles/): 4 x 16 B in flight per thread at 4 CTAs x 512 threads per SM.
 int copy_unroll() {
-  static const int u = [] {
-    const char* e = getenv("B200DDP_COPY_UNROLL");
-    const int v = e ? atoi(e) : 4;
-    return (v == 2 || v == 8) ? v : 4;
-  }();
-  return u;
+  const char* e = getenv("B200DDP_COPY_UNROLL");  // read per launch (like B200DDP_COPY_SPLIT): tools/ab_copy.py flips it
+  const int v = e ? atoi(e) : 4;
+  return (v == 2 || v == 8) ? v : 4;
 }
 
 template <int DT, int UNROLL>

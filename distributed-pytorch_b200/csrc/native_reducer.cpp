@@ -147,6 +147,15 @@ class NativeReducer {
     armed_ = false;
   }
 
+  // an armed iteration that will never finish (aborted graph capture): forget it
+  void abort() {
+    std::lock_guard<std::mutex> lk(mu_);
+    armed_ = false;
+    unfinished_ = false;
+    callback_queued_ = false;
+    keepalive_.clear();
+  }
+
   std::vector<int64_t> take_ready_order() {
     std::lock_guard<std::mutex> lk(mu_);
     record_order_ = false;
@@ -321,6 +330,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("rebind", &NativeReducer::rebind)
       .def("prepare", &NativeReducer::prepare, py::call_guard<py::gil_scoped_release>())
       .def("disarm", &NativeReducer::disarm)
+      .def("abort", &NativeReducer::abort)
       .def("take_ready_order", &NativeReducer::take_ready_order)
       .def("iterations", &NativeReducer::iterations)
       .def("launches", &NativeReducer::launches)

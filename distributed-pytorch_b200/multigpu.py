@@ -47,6 +47,7 @@ class Trainer(TrainerCore):
 
     def _save_checkpoint(self, epoch: int) -> None:
         """Rank 0 writes the UN-wrapped weights (``.module``), like ref:multigpu.py:53-56."""
+        self._check_health()  # never save weights that took a step on a timed-out (un-averaged) bucket
         torch.save(self.model.module.state_dict(), CHECKPOINT_PATH)
         print(f"Epoch {epoch} | Training checkpoint saved at {CHECKPOINT_PATH}")
 

@@ -118,6 +118,7 @@ class Trainer:
             prof.stop()
 
     def save_checkpoint(self, path: str = "model_ddp.pth") -> None:
+        self.model.check_health()  # never save weights that took a step on a timed-out (un-averaged) bucket
         torch.save(self.model.state_dict(), path)  # the WRAPPED state dict: keys carry the module. prefix
         print(f"Model state dict saved at {path}")
 

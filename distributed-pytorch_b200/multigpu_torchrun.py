@@ -50,6 +50,7 @@ class Trainer(TrainerCore):
         print(f"Resuming training from snapshot at Epoch {self.epochs_run}")
 
     def _save_snapshot(self, epoch: int) -> None:
+        self._check_health()  # never save weights that took a step on a timed-out (un-averaged) bucket
         torch.save({"EPOCHS_RUN": epoch, "MODEL_STATE": self.model.module.state_dict()}, self.snapshot_path)
         print(f"Epoch {epoch} | Training snapshot saved at {self.snapshot_path}")
 

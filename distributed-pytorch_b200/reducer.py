@@ -419,6 +419,15 @@ class Reducer:
                         b.algo, b.fused, views))
         return out
 
+    def abort_iteration(self) -> None:
+        """Forget an iteration that was armed but will never finish (an aborted CUDA-graph capture): the next
+        forward starts clean.  Nothing was executed on the device, so no rank is left waiting."""
+        self.armed = False
+        self._unfinished = False
+        self._callback_queued = False
+        if self._native is not None:
+            self._native.abort()
+
     def disarm(self) -> None:
         """The coming backward must not reduce (no_sync, or a forward without grad)."""
         self.armed = False

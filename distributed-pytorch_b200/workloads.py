@@ -125,6 +125,11 @@ WORKLOADS = {
                                                            nn.Linear(256, 7)).to(torch.bfloat16),
                          lambda b, device, gen=None: tuple(t.to(torch.bfloat16) for t in _rows(20, 7)(b, device, gen)),
                          F.mse_loss, torch.bfloat16),
+    # the GPT-2-medium shape cut to 2 layers for parity tests: same tensor shapes and bucket structure per layer,
+    # the same 103 MB tied-embedding bucket, a fraction of the time
+    "gpt2m_2l": Workload("gpt2m_2l", lambda: GPT2Shaped(layers=2).to(torch.bfloat16),
+                         lambda b, device, gen=None: tuple(t[:, :128] for t in _tokens(b, device, gen)), _lm_loss,
+                         torch.bfloat16, 8),
     # small multi-bucket model for parity tests
     "mlp": Workload("mlp", lambda: nn.Sequential(nn.Linear(20, 96), nn.ReLU(), nn.Linear(96, 96), nn.ReLU(),
                                                  nn.Linear(96, 7)), _rows(20, 7), F.mse_loss),

@@ -74,12 +74,14 @@ def raw_allreduce(rank, world, mem="vmm"):
     return res
 
 
-def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None, views=False):
+def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None, views=False, batch=16):
     """Our DDP and stock torch-DDP/NCCL side by side: same seeded weights, same per-rank batches."""
     import copy
 
     from b200ddp import DDP, workloads
 
+    if workload == "resnet50":  # parity needs the two replicas' backward kernels to be the same ones
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
     wl = workloads.get(workload)
     dev = torch.device("cuda", rank)
     torch.manual_seed(4321)
@@ -93,7 +95,7 @@ def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None, views=
     gen = torch.Generator().manual_seed(99 + rank)
     worst = 0.0
     for step in range(steps):
-        x, y = wl.batch(16, dev, gen)
+        x, y = wl.batch(batch, dev, gen)
         ref_m.load_state_dict(ours_m.state_dict())  # same weights going into every step
         o1.zero_grad()
         o2.zero_grad()
@@ -115,7 +117,43 @@ def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None, views=
     return res
 
 
-FUNCS = dict(raw_allreduce=raw_allreduce, ddp_vs_nccl=ddp_vs_nccl)
+def hook_vs_nccl(rank, world, workload="slices", steps=3):
+    """Stock torch DDP with our allreduce as its comm hook (hooks.allreduce_hook) against stock torch DDP: the
+    dependency's own plugin API for the step (SURVEY §8 b).  Same weights, same batches."""
+    import copy
+
+    from b200ddp import hooks, workloads
+
+    wl = workloads.get(workload)
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(4321)
+    base = wl.build().to(dev)
+    a, b = copy.deepcopy(base), copy.deepcopy(base)
+    stock = torch.nn.parallel.DistributedDataParallel(a, device_ids=[rank])
+    hooked = torch.nn.parallel.DistributedDataParallel(b, device_ids=[rank])
+    state = hooks.AllreduceState(rank, staging_mb=16)  # the 64 MiB first-iteration bucket is chunked
+    hooked.register_comm_hook(state, hooks.allreduce_hook)
+    gen = torch.Generator().manual_seed(99 + rank)
+    worst = 0.0
+    for step in range(steps):
+        x, y = wl.batch(16, dev, gen)
+        for m in (stock, hooked):
+            m.zero_grad()
+            wl.loss(m(x), y).backward()
+        torch.cuda.synchronize()
+        for p, q in zip(b.parameters(), a.parameters()):
+            denom = float(q.grad.double().abs().max())
+            num = float((p.grad.double() - q.grad.double()).abs().max())
+            worst = max(worst, num / denom if denom > 0 else num)
+    res = dict(worst_rel=worst, buckets_reduced=state.buckets_reduced, has_multicast=state.comm.has_multicast)
+    torch.cuda.synchronize()
+    dist.barrier()
+    del stock, hooked
+    state.close()
+    return res
+
+
+FUNCS = dict(raw_allreduce=raw_allreduce, ddp_vs_nccl=ddp_vs_nccl, hook_vs_nccl=hook_vs_nccl)
 
 
 def entry(rank, world, port, fn_name, kw, ret):

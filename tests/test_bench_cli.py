@@ -47,3 +47,21 @@ def test_product_arm_without_gpu_fails_loudly():
     out = _run({}, "--gpus", "1", "--steps", "3", "--warmup", "1", timeout=100)
     assert out.returncode != 0
     assert "no CPU fallback" in out.stdout or "no CUDA" in out.stdout
+
+
+def test_bench_helpers_blocks_and_identical_config():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    # the driver passes --steps 20: thirty blocks of 20 replace one sub-millisecond sample
+    assert bench.blocks_for("toy", 20, None) == 30
+    assert bench.blocks_for("toy", 2000, None) == 1
+    assert bench.blocks_for("resnet50", 20, None) == 2
+    assert bench.blocks_for("gpt2m", 10, 4) == 4
+    # `config` is the same dict in every arm (implementation details live in impl_config)
+    cfg = bench.bench_config("toy", 8, 32)
+    assert cfg == {"workload": bench.WORKLOAD_DESC["toy"], "global_batch": 256, "parallelism": "dp8", "l2": bench.L2_NOTE}
+    st = bench.block_stats([3.0, 1.0, 2.0], 20)
+    assert st == {"timed_blocks": 3, "block_ms_min": 1.0, "block_ms_median": 2.0, "block_ms_max": 3.0, "steps_per_block": 20}

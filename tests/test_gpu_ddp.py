@@ -29,8 +29,10 @@ def pg1():
     destroy_process_group()
 
 
-def test_trainer_world1_matches_plain_training_bitwise(pg1):
+def test_trainer_world1_matches_plain_training_bitwise(pg1, monkeypatch):
     from b200ddp import multigpu, utils
+
+    monkeypatch.setenv("B200DDP_GRAPH", "0")  # every step eager: one launch of ours per step is counted below
 
     torch.manual_seed(0)
     ds = utils.MyTrainDataset(256, seed=3)
@@ -275,19 +277,23 @@ def test_loopback_ws2_graph_replay_stays_in_step():
             with torch.cuda.stream(streams[r]):
                 trainers[r]._eager_step(*data[r][0])
     torch.cuda.synchronize()
-    graphs = []
+    from b200ddp._trainer_core import _signature, _Slot
+
     for r in range(2):
         t = trainers[r]
-        t._g_source, t._g_targets = data[r][0][0].clone(), data[r][0][1].clone()
+        slot = _Slot()
+        slot.source, slot.targets = data[r][0][0].clone(), data[r][0][1].clone()
         t.optimizer.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=streams[r]):
-            loss = t.loss_fn(t.model(t._g_source), t._g_targets)
+            loss = t.loss_fn(t.model(slot.source), slot.targets)
             loss.backward()
             t.optimizer.step()
-            t._g_loss = loss.detach()
-        t._graph = g
-        graphs.append(g)
+            slot.loss = loss.detach()
+        slot.graph = g
+        st = t._state()
+        st["mode"], st["sig"] = "on", _signature(slot.source, slot.targets)
+        st["slots"]["dev"] = slot
     ref = copy.deepcopy(trainers[0].model.module)
     ropt = torch.optim.SGD(ref.parameters(), lr=1e-2)
     for step in range(1, 6):
@@ -356,9 +362,333 @@ def test_multigpu_ddp_matches_stock_nccl_ddp(workload):
 
 @needs_multi
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("workload,batch,tol", [("resnet50", 8, 1e-6), ("gpt2m_2l", 2, 2e-2)])
+def test_multigpu_baseline_configs_match_stock_nccl_ddp(workload, batch, tol):
+    """BASELINE configs[3] (ResNet-50 fp32, 161 tensors, 5 buckets, soft-label CE — ref:multigpu_profile.py:25,49) and
+    configs[4]'s shape (GPT-2-medium tensors, bf16, 2 of the 24 layers + the tied 103 MB embedding) against stock
+    torch-DDP/NCCL on the same seeds.  fp32: north_star's 1e-6; bf16: measured and printed (NCCL sums in bf16, we
+    accumulate in fp32 and round once)."""
+    world = min(torch.cuda.device_count(), 8)
+    out = _spawn_mp("ddp_vs_nccl", world, workload=workload, steps=3, batch=batch)
+    worst = max(out[r]["worst_rel"] for r in range(world))
+    print(f"{workload} ws={world}: worst rel vs stock NCCL DDP = {worst:.3e}; buckets {out[0]['buckets']}; "
+          f"algos {out[0]['algos']}")
+    for r in range(world):
+        assert out[r]["worst_rel"] <= tol, out[r]
+        assert out[r]["weights_equal_across_ranks"]
+
+
+@needs_multi
+@pytest.mark.timeout(900)
+def test_multigpu_comm_hook_shim_matches_stock_nccl_ddp():
+    world = min(torch.cuda.device_count(), 8)
+    out = _spawn_mp("hook_vs_nccl", world)
+    print(f"comm hook ws={world}: worst rel vs stock NCCL DDP = {max(out[r]['worst_rel'] for r in range(world)):.3e}")
+    for r in range(world):
+        assert out[r]["worst_rel"] <= 1e-6, out[r]
+        assert out[r]["buckets_reduced"] >= 3
+
+
+@needs_multi
+@pytest.mark.timeout(900)
 def test_multigpu_gradient_as_bucket_view_matches_stock_nccl_ddp():
     world = min(torch.cuda.device_count(), 8)
     out = _spawn_mp("ddp_vs_nccl", world, workload="slices", views=True)
     for r in range(world):
         assert out[r]["worst_rel"] <= 1e-6, out[r]
         assert out[r]["weights_equal_across_ranks"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: the default script path (auto graph), the pipelined host path, the resident shard, the comm-hook shim,
+# and the BASELINE model shapes in 2-rank loop-back worlds (visible on a 1-GPU box)
+# ---------------------------------------------------------------------------------------------------
+def _plain_steps(plain, popt, batches, loss_fn=torch.nn.functional.mse_loss):
+    for x, y in batches:
+        popt.zero_grad()
+        loss_fn(plain(x), y).backward()
+        popt.step()
+
+
+def test_auto_graph_is_the_trainers_default_and_trains_like_eager(pg1, monkeypatch):
+    """B200DDP_GRAPH unset: three eager steps, then the step (incl. our fused bucket kernel) is replayed from a
+    CUDA graph; a batch of another shape (the partial batch that ends a shard) runs eagerly in between."""
+    from b200ddp import multigpu, utils
+
+    monkeypatch.delenv("B200DDP_GRAPH", raising=False)
+    torch.manual_seed(0)
+    ds = utils.MyTrainDataset(32 * 9 + 5, seed=11)
+    model = torch.nn.Linear(20, 1)
+    plain = copy.deepcopy(model).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    popt = torch.optim.SGD(plain.parameters(), lr=1e-2)
+    multigpu.Trainer.loss_fn = staticmethod(torch.nn.MSELoss())
+    try:
+        trainer = multigpu.Trainer(model, [], opt, 0, save_every=10**9)
+        xs, ys = ds.x.cuda(), ds.y.cuda()
+        batches = [(xs[i:i + 32], ys[i:i + 32]) for i in range(0, len(ds), 32)]
+        assert batches[-1][0].shape[0] == 5
+        losses = [trainer._run_batch(x, y) for x, y in batches[:6]]
+        st = trainer._state()
+        assert st["mode"] == "auto" and st["failed"] is None and st["slots"].get("dev") is not None
+        assert trainer.graph_kernel_launches == 1
+        trainer._run_batch(*batches[-1])  # partial batch: eager, the captured step stays
+        for x, y in batches[6:-1]:
+            losses.append(trainer._run_batch(x, y))
+        torch.cuda.synchronize()
+        _plain_steps(plain, popt, batches[:6] + [batches[-1]] + batches[6:-1])
+        for p, q in zip(trainer.model.module.parameters(), plain.parameters()):
+            assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+    finally:
+        multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
+
+
+def test_host_batches_go_through_the_pipelined_graphs(pg1, monkeypatch):
+    """Host (pinned) batches as the reference's DataLoader yields them: two alternating replays that start with
+    their own H2D copy and end with the loss D2H; every step's loss is readable one step late."""
+    from b200ddp import multigpu, utils
+    from b200ddp._trainer_core import PendingLoss
+
+    monkeypatch.setenv("B200DDP_GRAPH", "auto")
+    torch.manual_seed(0)
+    ds = utils.MyTrainDataset(32 * 12, seed=5)
+    model = torch.nn.Linear(20, 1)
+    plain = copy.deepcopy(model).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    popt = torch.optim.SGD(plain.parameters(), lr=1e-2)
+    multigpu.Trainer.loss_fn = staticmethod(torch.nn.MSELoss())
+    try:
+        trainer = multigpu.Trainer(model, [], opt, 0, save_every=10**9)
+        host = [(ds.x[i:i + 32].pin_memory(), ds.y[i:i + 32].pin_memory()) for i in range(0, len(ds), 32)]
+        got, want = [], []
+        for x, y in host:
+            out = trainer._run_batch(x, y)
+            got.append(out)
+        assert isinstance(got[-1], PendingLoss) and len(trainer._state()["slots"]["host"]) == 2
+        for x, y in host:
+            popt.zero_grad()
+            loss = torch.nn.functional.mse_loss(plain(x.cuda()), y.cuda())
+            loss.backward()
+            popt.step()
+            want.append(float(loss))
+        # a PendingLoss of an OLD step has been overwritten by a later replay of the same slot: only the last two
+        # are still meaningful, which is exactly the read-one-step-late protocol
+        assert abs(got[-1].item() - want[-1]) <= 1e-6 * max(1.0, abs(want[-1]))
+        assert abs(float(got[-2]) - want[-2]) <= 1e-6 * max(1.0, abs(want[-2]))
+        torch.cuda.synchronize()
+        for p, q in zip(trainer.model.module.parameters(), plain.parameters()):
+            assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+    finally:
+        multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
+
+
+def test_resident_shard_epoch_equals_loader_epoch(pg1, monkeypatch):
+    """B200DDP_RESIDENT=1: the script Trainer's epoch over the HBM-resident shard — one graph launch
+    per step, batch gathered by a device-side cursor, partial last batch eager — leaves the weights a plain
+    training loop over prepare_dataloader's batches leaves."""
+    from b200ddp import multigpu, utils
+
+    monkeypatch.setenv("B200DDP_RESIDENT", "1")
+    monkeypatch.delenv("B200DDP_GRAPH", raising=False)
+    torch.manual_seed(0)
+    ds = utils.MyTrainDataset(32 * 7 + 9, seed=21)
+    model = torch.nn.Linear(20, 1)
+    plain = copy.deepcopy(model).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    popt = torch.optim.SGD(plain.parameters(), lr=1e-2)
+    loader = multigpu.prepare_dataloader(ds, 32)
+    multigpu.Trainer.loss_fn = staticmethod(torch.nn.MSELoss())
+    try:
+        trainer = multigpu.Trainer(model, loader, opt, 0, save_every=10**9)
+        trainer.train(2)
+        torch.cuda.synchronize()
+        res = trainer._state()["resident"]
+        assert res is not None and res["steps"] == 7 and int(res["cursor"]) == 0
+        first = [(x.cuda(), y.cuda()) for x, y in loader]
+        # enable_resident_shard's two eager steps on the first batch precede the first epoch
+        _plain_steps(plain, popt, [first[0], first[0]] + first + first)
+        for p, q in zip(trainer.model.module.parameters(), plain.parameters()):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    finally:
+        multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
+
+
+@pytest.mark.timeout(300)
+def test_script_entry_point_reaches_graph_replay(tmp_path):
+    """`python multigpu.py <epochs> <save_every>` (ref:multigpu.py:91-96) with nothing but the defaults: the
+    training step is captured and replayed (B200DDP_GRAPH_STRICT turns a capture failure into an error)."""
+    import subprocess
+    import sys
+
+    from oracle.ref_ddp import free_port
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200DDP_VERBOSE="1", B200DDP_GRAPH_STRICT="1", MASTER_ADDR="127.0.0.1",
+               MASTER_PORT=str(free_port()), B200DDP_TIMEOUT_MS="30000")
+    env.pop("B200DDP_GRAPH", None)
+    out = subprocess.run([sys.executable, os.path.join(root, "distributed-pytorch_b200", "multigpu.py"), "2", "1"],
+                         capture_output=True, text=True, timeout=280, env=env, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "training step captured into a CUDA graph (kind=host" in out.stdout, out.stdout[-2000:]
+    assert "Epoch 1 | Training checkpoint saved" in out.stdout
+    assert os.path.exists(tmp_path / "checkpoint.pt")
+
+
+def test_comm_hook_shim_on_stock_ddp_world1(pg1):
+    """Stock torch DDP + register_comm_hook(AllreduceState(), allreduce_hook) (SURVEY §8 b, the dependency's own
+    plugin API): at world 1 the hook's flatten -> (no exchange) -> unflatten must hand back the bucket bit for bit,
+    also for the iteration-0 mega-bucket that is larger than the hook's staging area (chunked)."""
+    from b200ddp import hooks
+
+    torch.manual_seed(3)
+    base = torch.nn.Sequential(torch.nn.Linear(64, 1500), torch.nn.ReLU(), torch.nn.Linear(1500, 900), torch.nn.ReLU(),
+                               torch.nn.Linear(900, 10)).cuda()
+    a, b = copy.deepcopy(base), copy.deepcopy(base)
+    stock = torch.nn.parallel.DistributedDataParallel(a, device_ids=[0], bucket_cap_mb=1)
+    hooked = torch.nn.parallel.DistributedDataParallel(b, device_ids=[0], bucket_cap_mb=1)
+    state = hooks.AllreduceState(staging_mb=1)  # 1 MiB staging: the 5.8 MB first-iteration bucket is chunked
+    hooked.register_comm_hook(state, hooks.allreduce_hook)
+    gen = torch.Generator().manual_seed(1)
+    for step in range(3):
+        x = torch.rand(16, 64, generator=gen).cuda()
+        y = torch.rand(16, 10, generator=gen).cuda()
+        for m in (stock, hooked):
+            m.zero_grad()
+            torch.nn.functional.mse_loss(m(x), y).backward()
+        torch.cuda.synchronize()
+        for p, q in zip(a.parameters(), b.parameters()):
+            assert torch.equal(p.grad, q.grad), f"step {step}"
+    assert state.buckets_reduced >= 3 and state.comm.launch_count > 0
+    del stock, hooked
+    state.close()
+
+
+def _loopback_ddp_world(models, comms, streams, staging, **ddp_kw):
+    """One host thread drives every rank, so it must never block between launching rank 0's kernels and rank 1's:
+    all calls only enqueue, and callers run the ranks' forwards before the ranks' backwards (a rank's stream that
+    waits for its peer must not have to absorb a whole step's launches)."""
+    from b200ddp import DDP
+    from b200ddp.reducer import P2PEngine
+
+    dev = torch.device("cuda", 0)
+    ddps = []
+    for r, m in enumerate(models):
+        with torch.cuda.stream(streams[r]):
+            ddps.append(DDP(m, device_ids=[0], _engine=P2PEngine(dev, 0, comm=comms[r], staging_bytes=staging),
+                            **ddp_kw))
+    torch.cuda.synchronize()
+    return ddps
+
+
+def _loopback_step(ddps, models, streams, inputs, targets, loss_fn):
+    losses = []
+    for r in range(len(ddps)):
+        with torch.cuda.stream(streams[r]):
+            models[r].zero_grad()
+            losses.append(loss_fn(ddps[r](inputs[r]), targets[r]))
+    for r in range(len(ddps)):
+        with torch.cuda.stream(streams[r]):
+            losses[r].backward()
+    torch.cuda.synchronize()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("views", [False, True], ids=["copy-back", "grad-views"])
+def test_loopback_ws2_resnet50_step_matches_the_average_of_local_gradients(views):
+    """BASELINE configs[3] on ONE GPU: two ResNet-50 replicas (161 gradient tensors, 107 of them < 16 KiB, five
+    buckets of 8-30 MiB, per-forward BatchNorm buffer broadcast) in a 2-rank loop-back world.  Every parameter's
+    .grad must equal fl32(0.5)*g0 + fl32(0.5)*g1 of the un-wrapped replicas' local gradients within 1e-6 of the
+    tensor's max (north_star's tolerance), in iteration 0 (construction-time buckets) and after the rebuild."""
+    from torchvision.models import resnet50
+
+    from b200ddp.comm import P2PComm
+    from tests.helpers import rel_err
+
+    old = torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    comms = P2PComm.loopback_world(2, 0, 320 << 20)
+    try:
+        for c in comms:
+            c.set_timeout_ms(20000)
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        torch.manual_seed(0)
+        base = resnet50().cuda()
+        models = [copy.deepcopy(base) for _ in range(2)]
+        locals_ = [copy.deepcopy(base) for _ in range(2)]
+        ddps = _loopback_ddp_world(models, comms, streams, 16 << 20, gradient_as_bucket_view=views)
+        gen = torch.Generator().manual_seed(7)
+        worst = 0.0
+        for step in range(3):
+            xs = [torch.rand(4, 3, 96, 96, generator=gen).cuda() for _ in range(2)]
+            ys = [torch.rand(4, 1000, generator=gen).cuda() for _ in range(2)]
+            torch.cuda.synchronize()
+            for r in range(2):
+                locals_[r].load_state_dict(models[r].state_dict())
+                locals_[r].zero_grad()
+                torch.nn.functional.cross_entropy(locals_[r](xs[r]), ys[r]).backward()  # soft-label CE, ref:multigpu_profile.py:49
+            torch.cuda.synchronize()
+            _loopback_step(ddps, models, streams, xs, ys, torch.nn.functional.cross_entropy)
+            for c in comms:
+                c.poll_error()
+            half = torch.tensor(0.5, dtype=torch.float32, device="cuda")
+            for (n, p0), p1, l0, l1 in zip(models[0].named_parameters(), models[1].parameters(),
+                                           locals_[0].parameters(), locals_[1].parameters()):
+                want = l0.grad * half + l1.grad * half
+                assert torch.equal(p0.grad, p1.grad), f"ranks differ on {n}"
+                e = rel_err(p0.grad, want)
+                worst = max(worst, e)
+                assert e <= 1e-6, f"step {step} {n}: rel {e:.3e}"
+        sizes = ddps[0].reducer.bucket_sizes()
+        assert ddps[0].reducer.has_rebuilt and len(sizes) == 5 and max(sizes) > (25 << 20)
+        assert sum(len(b.param_indices) for b in ddps[0].reducer.buckets) == 161
+        print(f"resnet50 loop-back ws=2 (views={views}): worst rel vs average of local grads = {worst:.3e}")
+        for d in ddps:
+            d.shutdown()
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = old
+        torch.cuda.synchronize()
+
+
+@pytest.mark.timeout(600)
+def test_loopback_ws2_gpt2_shaped_bf16_step():
+    """BASELINE configs[4] shape, 2 layers: bf16 buckets (fp32 accumulate, one rounding) incl. the 103 MB tied
+    embedding bucket.  Reference = bf16(fl32(bf16(0.5 g0)) + fl32(bf16(0.5 g1))): what the reference computes with a
+    bf16 NCCL sum differs from ours by at most one bf16 rounding of the sum, so the bound is 2^-7 of the tensor max
+    (measured values are printed)."""
+    from b200ddp import workloads
+    from b200ddp.comm import P2PComm
+    from tests.helpers import rel_err
+
+    wl = workloads.get("gpt2m_2l")
+    comms = P2PComm.loopback_world(2, 0, 400 << 20)
+    for c in comms:
+        c.set_timeout_ms(20000)
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    torch.manual_seed(0)
+    base = wl.build().cuda()
+    models = [copy.deepcopy(base) for _ in range(2)]
+    locals_ = [copy.deepcopy(base) for _ in range(2)]
+    ddps = _loopback_ddp_world(models, comms, streams, 112 << 20)
+    gen = torch.Generator().manual_seed(3)
+    worst = 0.0
+    for step in range(2):
+        batches = [wl.batch(2, torch.device("cuda"), gen) for _ in range(2)]
+        torch.cuda.synchronize()
+        for r in range(2):
+            locals_[r].zero_grad()
+            wl.loss(locals_[r](batches[r][0]), batches[r][1]).backward()
+        torch.cuda.synchronize()
+        _loopback_step(ddps, models, streams, [b[0] for b in batches], [b[1] for b in batches], wl.loss)
+        for c in comms:
+            c.poll_error()
+        for (n, p0), p1, l0, l1 in zip(models[0].named_parameters(), models[1].parameters(), locals_[0].parameters(),
+                                       locals_[1].parameters()):
+            assert torch.equal(p0.grad, p1.grad), f"ranks differ on {n}"
+            want = ((l0.grad.float() * 0.5).bfloat16().float() + (l1.grad.float() * 0.5).bfloat16().float()).bfloat16()
+            e = rel_err(p0.grad, want)
+            worst = max(worst, e)
+            assert e <= 2.0 ** -7, f"step {step} {n}: rel {e:.3e}"
+    assert max(ddps[0].reducer.bucket_sizes()) > (100 << 20)
+    print(f"gpt2-shaped bf16 loop-back ws=2: worst rel vs fp32-accumulated average = {worst:.3e}")
+    for d in ddps:
+        d.shutdown()

@@ -334,6 +334,76 @@ def test_missing_peer_times_out_instead_of_hanging():
         w.close()
 
 
+def test_timeout_poisons_the_rank_and_gradients_are_left_alone():
+    """after a peer timeout a kernel must not scatter a partial sum.  Rank 1 never launches: rank 0's
+    allreduce times out, the unflatten that follows it leaves the gradient untouched, the rank stays poisoned
+    (later launches return at once instead of waiting for another timeout), and the host sees the error."""
+    import time
+
+    w = World(2, arena=1 << 20)
+    try:
+        c0 = w.comms[0]
+        c0.set_timeout_ms(200)
+        s = torch.cuda.Stream().cuda_stream
+        gen = torch.Generator().manual_seed(5)
+        g = _rand(1000, "f32", gen)
+        before = g.clone()
+        table = TensorTable([g.data_ptr()], [0], [1000])
+        c0.flatten_scale(table, _lib.F32, 0, 0.5, s)
+        c0.allreduce(0, 0, 4000, _lib.F32, _lib.ALGO_TWOSHOT, 1, s)
+        c0.unflatten(table, _lib.F32, 0, s)
+        torch.cuda.synchronize()
+        assert torch.equal(g, before), "unflatten scattered a bucket whose allreduce had timed out"
+        assert torch.equal(c0.view(0, 4000, torch.float32), before * 0.5)  # the flatten itself did run
+        small = [_rand(20, "f32", gen), _rand(1, "f32", gen)]
+        keep = [t.clone() for t in small]
+        c0.clear(8192, c0.fused_region_bytes(96), s)
+        t0 = time.perf_counter()
+        c0.fused_bucket(TensorTable([t.data_ptr() for t in small], [0, 20], [20, 1]), _lib.F32, 8192, 96, 0.5, s)
+        c0.allreduce(0, 0, 4000, _lib.F32, _lib.ALGO_TWOSHOT_TMA, 1, s)
+        torch.cuda.synchronize()
+        assert time.perf_counter() - t0 < 0.15, "a poisoned rank must not wait for another timeout"
+        for t, k in zip(small, keep):
+            assert torch.equal(t, k)
+        with pytest.raises(RuntimeError, match="timed out"):
+            c0.poll_error()
+    finally:
+        w.close()
+
+
+def test_allreduce_scale_is_applied_to_the_reduced_sum(world):
+    """`scale` of b200ddp_allreduce (the comm-hook shim's 1/world): out = fl32(scale * sum), one extra rounding."""
+    n = 4 * 3001
+    bufs = world.fill(0, n, "f32", seed=9)
+    want = ao.allreduce_sum(bufs, "f32") * np.float32(0.25)
+    for name, algo in ALGOS.items():
+        world.fill(0, n, "f32", seed=9)
+        out_off = (1 << 20) if name == "oneshot" else 0
+        world.run(lambda r, c, s: c.allreduce(0, out_off, n * 4, _lib.F32, algo, 4, s, scale=0.25))
+        for c in world.comms:
+            assert np.array_equal(_storage(c.view(out_off, n * 4, torch.float32), "f32"), want), name
+
+
+def test_world1_allreduce_with_scale_scales_in_place(comm1):
+    gen = torch.Generator().manual_seed(2)
+    t = _rand(4 * 777, "f32", gen)
+    comm1.view(0, t.numel() * 4, torch.float32).copy_(t)
+    s = torch.cuda.current_stream().cuda_stream
+    comm1.allreduce(0, 0, t.numel() * 4, _lib.F32, _lib.ALGO_AUTO, 0, s, scale=0.125)
+    torch.cuda.synchronize()
+    assert torch.equal(comm1.view(0, t.numel() * 4, torch.float32), t * 0.125)
+
+
+def test_peer_read_copies_a_peers_arena(world):
+    n = 4 * 5003
+    bufs = world.fill(0, n, "f32", seed=4)
+    peer = (0 + 1) % world.ws
+    c0, s0 = world.comms[0], world.streams[0].cuda_stream
+    c0.peer_read(peer, 0, 1 << 20, n * 4, s0, 4)
+    torch.cuda.synchronize()
+    assert np.array_equal(_storage(c0.view(1 << 20, n * 4, torch.float32), "f32"), bufs[peer])
+
+
 def test_allreduce_argument_validation(world):
     c = world.comms[0]
     s = world.streams[0].cuda_stream

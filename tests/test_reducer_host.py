@@ -256,3 +256,93 @@ def test_buffer_sync_flag_follows_the_previous_forward():
     plain = DDP(nn.Sequential(nn.Linear(4, 4), nn.BatchNorm1d(4)), broadcast_buffers=False, _engine=Counting())
     plain(x).sum().backward()
     assert plain.engine.bcasts == 1
+
+
+def test_arena_is_sized_from_the_construction_time_plan():
+    """the arena must not double the gradient memory.  ResNet-50 (fp32, 161 tensors) and a
+    GPT-2-medium-shaped bf16 parameter list: arena <= 1.07 x payload + 8 MiB at world 8 (round 1 reserved
+    2 x payload + 1 MiB of LL slots per large parameter)."""
+    from b200ddp.reducer import arena_bytes_for
+
+    def fake(numels, dtype):
+        return [torch.empty(n, dtype=dtype, device="meta").requires_grad_() for n in numels]
+
+    from torchvision.models import resnet50
+
+    with torch.device("meta"):
+        m = resnet50()
+    ps = list(m.parameters())
+    payload = sum(p.numel() * 4 for p in ps)
+    got = arena_bytes_for(ps, world_size=8)
+    assert payload < got <= int(1.07 * payload) + (8 << 20)
+    # bf16 transformer: 24 x (qkv, proj, fc1, fc2 + norms), tied 50257 x 1024 embedding
+    numels = [50257 * 1024, 1024 * 1024]
+    for _ in range(24):
+        numels += [1024, 1024, 3 * 1024 * 1024, 3 * 1024, 1024 * 1024, 1024, 1024, 1024, 4096 * 1024, 4096, 4096 * 1024, 1024]
+    ps = fake(numels, torch.bfloat16)
+    payload = sum(numels) * 2
+    got = arena_bytes_for(ps, world_size=8)
+    assert payload < got <= int(1.07 * payload) + (8 << 20)
+    # the toy model: one 84-byte bucket on the LL path: 4 * ws * 96 bytes of slots, nothing like megabytes per tensor
+    toy = fake([20, 1], torch.float32)
+    assert arena_bytes_for(toy, world_size=8) <= (2 << 20) + 8192
+    # small caps put every bucket on the fused (double-buffered) path: two slots each
+    small = arena_bytes_for(fake([30000] * 8, torch.float32), world_size=2, bucket_bytes_cap=100_000,
+                            first_bucket_bytes_cap=100_000)
+    assert small >= 2 * 8 * 30000 * 4
+
+
+def test_trainer_graph_mode_state_machine_without_a_gpu(monkeypatch, capsys):
+    """B200DDP_GRAPH semantics of TrainerCore: `0` is always eager; `auto` runs GRAPH_AFTER eager steps of one
+    batch shape, then tries to capture — which cannot work on this CPU box, so the Trainer must report it once
+    and keep training eagerly (the same fallback a non-capturable model takes on the GPU)."""
+    from b200ddp._trainer_core import TrainerCore
+
+    def make(mode):
+        if mode is None:
+            monkeypatch.delenv("B200DDP_GRAPH", raising=False)
+        else:
+            monkeypatch.setenv("B200DDP_GRAPH", mode)
+        t = TrainerCore()
+        t.model = nn.Linear(4, 1)
+        t.optimizer = torch.optim.SGD(t.model.parameters(), lr=0.1)
+        t.loss_fn = nn.functional.mse_loss
+        t.gpu_id = "cpu"
+        return t
+
+    x, y = torch.randn(8, 4), torch.randn(8, 1)
+    t = make("0")
+    for _ in range(6):
+        assert isinstance(t._run_batch(x, y), torch.Tensor)
+    assert t._state()["eager_run"] == 0 and t._state()["failed"] is None
+    t = make(None)
+    assert t._state()["mode"] == "auto"
+    w0 = t.model.weight.detach().clone()
+    for i in range(6):
+        loss = t._run_batch(x, y)
+        assert isinstance(loss, torch.Tensor)
+        if i == 2:
+            assert t._state()["failed"] is None and t._state()["eager_run"] == TrainerCore.GRAPH_AFTER
+    assert t._state()["failed"] is not None and not t._state()["slots"]  # capture was attempted once, then eager
+    assert "continuing eagerly" in capsys.readouterr().out
+    assert not torch.equal(t.model.weight, w0)
+    # a different batch shape before capture restarts the count
+    t = make(None)
+    t._run_batch(x, y)
+    t._run_batch(x[:3], y[:3])
+    assert t._state()["eager_run"] == 1
+    with pytest.raises(ValueError, match="B200DDP_GRAPH"):
+        make("sometimes")._state()
+
+
+def test_comm_hook_has_the_signature_torch_checks():
+    """torch's _check_comm_hook (nn/parallel/distributed.py:2268-2289) looks the parameter up by the literal name
+    `bucket` and compares annotation OBJECTS."""
+    import torch.distributed as dist
+
+    from b200ddp import hooks
+
+    sig = inspect.signature(hooks.allreduce_hook)
+    assert list(sig.parameters) == ["state", "bucket"]
+    assert sig.parameters["bucket"].annotation is dist.GradBucket
+    assert sig.return_annotation == torch.futures.Future[torch.Tensor]

@@ -26,17 +26,17 @@ torch.cuda.synchronize()
 for i in range(4):
     comm.flatten_scale(tables[i], _lib.F32, 0, 0.125, stream.cuda_stream)
     comm.unflatten(tables[(i + 1) % 4], _lib.F32, 0, stream.cuda_stream)
-# ResNet-50-like bucket: 100 small tensors + a few large ones (slow path + fast path in one launch)
-lens = [256 + 64 * (i % 13) for i in range(100)] + [2359296, 1048576, 589824]
-ts = [torch.rand(n, device="cuda") for n in lens]
-o, offs2 = 0, []
-for n in lens:
-    offs2.append(o)
-    o += (n + 3) // 4 * 4
-t2 = TensorTable([t.data_ptr() for t in ts], offs2, lens)
-for _ in range(2):
-    comm.flatten_scale(t2, _lib.F32, 0, 0.125, stream.cuda_stream)
-    comm.unflatten(t2, _lib.F32, 0, stream.cuda_stream)
+# the largest real ResNet-50 bucket (bench.resnet_table: two 9 MiB convolutions + dozens of 256 B - 8 KiB
+# BatchNorm vectors): boundary tiles and straight tiles in one launch
+import bench  # noqa: E402
+
+S2, n_t2, tables2, keep2 = bench.resnet_table(torch, TensorTable, torch.device("cuda", 0), 4)
+comm2 = P2PComm(0, 1, 0, S2 + (1 << 20), _lib.MEM_AUTO)
+for i in range(4):
+    comm2.flatten_scale(tables2[i], _lib.F32, 0, 0.125, stream.cuda_stream)
+    comm2.unflatten(tables2[(i + 1) % 4], _lib.F32, 0, stream.cuda_stream)
+torch.cuda.synchronize()
+comm2.destroy()
 # the toy model's 84-byte bucket through the fused kernel (world 1)
 g = [torch.rand(20, device="cuda"), torch.rand(1, device="cuda")]
 t3 = TensorTable([x.data_ptr() for x in g], [0, 20], [20, 1])
