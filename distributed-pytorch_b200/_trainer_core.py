@@ -264,15 +264,33 @@ class TrainerCore:
         slot.targets = slot.dev_pack[t_off:t_off + tb].view(targets.dtype).view(targets.shape)
         slot.host_source.copy_(source)
         slot.host_targets.copy_(targets)
-        slot.host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+        slot.host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
         slot.done = torch.cuda.Event()
+        # Small batches (the toy rows: 2.7 KB) cross PCIe inside copy KERNELS that read / write the pinned buffers
+        # through their device mapping (pinned memory is device-addressable under unified addressing): a
+        # copy-engine memcpy node costs ~7 us of graph time per transfer at this size, a kernel node ~2 us.  Large
+        # batches (ResNet-50: 19 MB) keep the copy engine.  B200DDP_STAGE=memcpy|kernel forces one.
+        how = os.environ.get("B200DDP_STAGE", "auto").lower()
+        mapped = how == "kernel" or (how != "memcpy" and slot.host_pack.numel() <= (64 << 10))
+        src_alias = loss_alias = None
+        if mapped:
+            from .comm import _CudaArray
+
+            src_alias = torch.as_tensor(_CudaArray(slot.host_pack.data_ptr(), slot.host_pack.numel()), device=dev)
+            loss_alias = torch.as_tensor(_CudaArray(slot.host_loss.data_ptr(), 4), device=dev).view(torch.float32)
 
         def prologue():
-            slot.dev_pack.copy_(slot.host_pack, non_blocking=True)
+            if mapped:
+                slot.dev_pack.copy_(src_alias)  # H2D: a kernel reading the pinned staging buffer over PCIe
+            else:
+                slot.dev_pack.copy_(slot.host_pack, non_blocking=True)  # H2D: copy-engine memcpy node
             return slot.source, slot.targets
 
         def epilogue(loss: torch.Tensor) -> None:
-            slot.host_loss.copy_(loss.float(), non_blocking=True)
+            if mapped:
+                loss_alias.copy_(loss.float().reshape(1))  # D2H: a 4-byte store into pinned host memory
+            else:
+                slot.host_loss.copy_(loss.float().reshape(1), non_blocking=True)
 
         slot.graph, slot.loss = self._capture_step(prologue, epilogue)
         slot.done.record()
@@ -327,15 +345,36 @@ class TrainerCore:
                 self._eager_step(loader.x[:bsz], loader.y[:bsz])
             st["eager_run"] += 2
         res = {"loader": loader, "bsz": bsz, "full": full, "steps": full // bsz,
-               "cursor": torch.zeros((), dtype=torch.int64, device=dev),
-               "lane": torch.arange(bsz, dtype=torch.int64, device=dev)}
+               "cursor": torch.zeros((), dtype=torch.int64, device=dev)}
+        x, y = loader.x, loader.y
+        packed = (x.dim() == 2 and y.dim() == 2 and x.dtype == y.dtype and x.element_size() == 4)
+        if packed:
+            # rows of [source | targets] gathered by ONE launch of our gather kernel (b200ddp_gather_rows), which
+            # also advances the cursor: the replayed step starts with a single extra node
+            from . import _lib
 
-        def prologue():
-            idx = res["lane"] + res["cursor"]
-            return loader.x.index_select(0, idx), loader.y.index_select(0, idx)
+            lib = _lib.load()
+            fx = x.shape[1]
+            res["xy"] = torch.cat([x[:full], y[:full]], dim=1).contiguous()
+            res["batch"] = torch.empty(bsz, res["xy"].shape[1], dtype=x.dtype, device=dev)
 
-        def epilogue(_loss: torch.Tensor) -> None:
-            res["cursor"].add_(bsz).remainder_(full)
+            def prologue():
+                rc = lib.b200ddp_gather_rows(res["xy"].data_ptr(), res["batch"].data_ptr(),
+                                             res["xy"].shape[1] * 4, bsz, full, res["cursor"].data_ptr(),
+                                             torch.cuda.current_stream(dev).cuda_stream)
+                _lib.check(rc, None, "gather_rows")
+                return res["batch"][:, :fx], res["batch"][:, fx:]
+
+            epilogue = None
+        else:
+            res["lane"] = torch.arange(bsz, dtype=torch.int64, device=dev)
+
+            def prologue():
+                idx = res["lane"] + res["cursor"]
+                return x.index_select(0, idx), y.index_select(0, idx)
+
+            def epilogue(_loss: torch.Tensor) -> None:
+                res["cursor"].add_(bsz).remainder_(full)
 
         try:
             res["graph"], res["loss"] = self._capture_step(prologue, epilogue)
@@ -345,6 +384,8 @@ class TrainerCore:
             if reducer is not None and hasattr(reducer, "abort_iteration"):
                 reducer.abort_iteration()
             return False
+        if packed:
+            self.graph_kernel_launches += 1  # gather_rows_kernel is ours too (it has no context to count it)
         res["cursor"].zero_()
         st["resident"] = res
         return True

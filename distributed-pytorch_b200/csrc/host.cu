@@ -1058,6 +1058,22 @@ int b200ddp_peer_read(b200ddp_ctx* c, int peer, uint64_t src_off, uint64_t dst_o
   return 0;
 }
 
+int b200ddp_gather_rows(const void* src, void* dst, uint64_t row_bytes, uint32_t batch_rows, uint64_t full_rows,
+                        void* cursor, void* stream) {
+  if (!src || !dst || !cursor) return fail(nullptr, B200DDP_EINVAL, "gather_rows: null pointer");
+  if (row_bytes == 0 || (row_bytes & 3) || batch_rows == 0 || full_rows == 0 || row_bytes * batch_rows > (64u << 20) ||
+      (reinterpret_cast<uint64_t>(src) & 3) || (reinterpret_cast<uint64_t>(dst) & 3) ||
+      (reinterpret_cast<uint64_t>(cursor) & 7))
+    return fail(nullptr, B200DDP_EINVAL, "gather_rows: rows must be whole 4-byte words, batch <= 64 MiB, aligned pointers");
+  cudaError_t e = launch_gather_rows(src, dst, static_cast<uint32_t>(row_bytes / 4), batch_rows, full_rows, cursor,
+                                     static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(nullptr, B200DDP_ECUDA, "gather_rows launch failed: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 int b200ddp_clear(b200ddp_ctx* c, uint64_t off, uint64_t nbytes, void* stream) {
   int rc = check_ready(c);
   if (rc) return rc;

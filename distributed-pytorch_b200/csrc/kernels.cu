@@ -414,6 +414,25 @@ __global__ void __launch_bounds__(512) local_copy_kernel(uint4* __restrict__ dst
 }
 
 // ---------------------------------------------------------------------------------------------------
+// input pipeline: the next batch of a device-resident shard, gathered by a device-side cursor.
+// dst[b] = src[(cursor + b) mod full_rows] for b < batch_rows (rows of row_words 4-byte words), then
+// cursor = (cursor + batch_rows) mod full_rows.  One launch, no host state: a captured training step replays it.
+// Single CTA: every thread reads the cursor before the barrier, thread 0 advances it after.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                          uint32_t row_words, uint32_t batch_rows, uint64_t full_rows,
+                                                          unsigned long long* cursor) {
+  const uint64_t cur = *reinterpret_cast<volatile unsigned long long*>(cursor) % full_rows;
+  __syncthreads();
+  const uint32_t total = batch_rows * row_words;
+  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const uint32_t b = i / row_words, k = i - b * row_words;
+    dst[i] = src[((cur + b) % full_rows) * row_words + k];
+  }
+  if (threadIdx.x == 0) *cursor = (cur + batch_rows) % full_rows;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // one-shot allreduce: every rank reads the whole bucket from every peer (small buckets, latency bound)
 // ---------------------------------------------------------------------------------------------------
 constexpr int kArThreads = 512;
@@ -1003,6 +1022,13 @@ cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, int max
   return cudaGetLastError();
 }
 
+cudaError_t launch_gather_rows(const void* src, void* dst, uint32_t row_words, uint32_t batch_rows, uint64_t full_rows,
+                               void* cursor, cudaStream_t s) {
+  gather_rows_kernel<<<1, 256, 0, s>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), row_words,
+                                       batch_rows, full_rows, static_cast<unsigned long long*>(cursor));
+  return cudaGetLastError();
+}
+
 cudaError_t launch_oneshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
                            int dtype, int max_ctas, float scale, cudaStream_t s) {
   const int grid = clamp_grid((nvec + kArThreads - 1) / kArThreads, max_ctas, 36);
@@ -1151,6 +1177,7 @@ cudaError_t prepare_dt(int world) {
 cudaError_t prepare_kernels(int world) {
   cudaError_t e;
   if ((e = preload(local_copy_kernel)) != cudaSuccess) return e;
+  if ((e = preload(gather_rows_kernel)) != cudaSuccess) return e;
   if ((e = preload(broadcast_kernel)) != cudaSuccess) return e;
   if ((e = preload(barrier_kernel)) != cudaSuccess) return e;
   if ((e = prepare_dt<B200DDP_F32>(world)) != cudaSuccess) return e;

@@ -74,16 +74,22 @@ class NativeReducer {
     scale_ = 1.0f / static_cast<float>(world_);
     param_bucket_.assign(params_.size(), -1);
     seen_.assign(params_.size(), 0);
-    for (size_t i = 0; i < params_.size(); ++i) {
+    for (size_t i = 0; i < params_.size(); ++i)
       if (!params_[i].requires_grad()) throw std::runtime_error("every reduced parameter must require a gradient");
-      auto acc = torch::autograd::impl::grad_accumulator(params_[i]);
-      const uintptr_t key = acc->add_post_hook(std::make_unique<torch::autograd::utils::LambdaPostHook>(
-          [this, i](const torch::autograd::variable_list& outputs, const torch::autograd::variable_list&) {
-            this->autograd_hook(i);
-            return outputs;
-          }));
-      hooks_.emplace_back(key, acc);  // keeps the accumulator (and so the hook) alive, like Reducer::hooks_
-    }
+    install_hooks();
+  }
+
+  // (Re-)create the AccumulateGrad nodes and hang the post hooks on them.  An AccumulateGrad node remembers the
+  // stream that was current when it was CREATED and the engine runs it there; torch's own Reducer keeps its nodes
+  // for good, which is why stock DDP must be constructed under the stream later forwards use (and why a DDP built
+  // on the default stream cannot be captured into a CUDA graph).  We instead re-create the nodes whenever the
+  // forward's stream changes (DDP.forward -> Reducer.bind_stream): eager steps, a capture on torch's capture
+  // stream, eager steps again — each with nodes of its own stream.  Only legal between iterations.
+  void rehook() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (armed_) throw std::runtime_error("cannot re-create the gradient accumulators while a backward is in flight");
+    remove_hooks();  // drops our references: nodes no graph holds any more are destroyed here
+    install_hooks();
   }
 
   ~NativeReducer() { remove_hooks(); }
@@ -172,6 +178,18 @@ class NativeReducer {
   }
 
  private:
+  void install_hooks() {
+    for (size_t i = 0; i < params_.size(); ++i) {
+      auto acc = torch::autograd::impl::grad_accumulator(params_[i]);
+      const uintptr_t key = acc->add_post_hook(std::make_unique<torch::autograd::utils::LambdaPostHook>(
+          [this, i](const torch::autograd::variable_list& outputs, const torch::autograd::variable_list&) {
+            this->autograd_hook(i);
+            return outputs;
+          }));
+      hooks_.emplace_back(key, acc);  // keeps the accumulator (and so the hook) alive, like Reducer::hooks_
+    }
+  }
+
   [[noreturn]] void fail(const char* what, int rc) {
     const char* msg = last_error_ ? last_error_(ctx_) : "";
     throw std::runtime_error(std::string("b200ddp ") + what + " failed (code " + std::to_string(rc) + "): " + (msg ? msg : ""));
@@ -328,6 +346,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("ctx"), py::arg("fns"), py::arg("world"), py::arg("comm_stream"), py::arg("max_ctas"), py::arg("params"))
       .def("configure", &NativeReducer::configure)
       .def("rebind", &NativeReducer::rebind)
+      .def("rehook", &NativeReducer::rehook)
       .def("prepare", &NativeReducer::prepare, py::call_guard<py::gil_scoped_release>())
       .def("disarm", &NativeReducer::disarm)
       .def("abort", &NativeReducer::abort)

@@ -156,6 +156,7 @@ class DistributedDataParallel(nn.Module):
         check = getattr(self.engine, "check_health", None)
         if check is not None:
             check(False)  # one host read: a timeout of the previous step surfaces before the next one starts
+        self.reducer.bind_stream()
         if self.device_ids is not None:
             inputs, kwargs = _move(inputs, self.device), _move(kwargs, self.device)
         if self.require_forward_param_sync and self.broadcast_buffers:

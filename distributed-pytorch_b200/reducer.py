@@ -382,6 +382,7 @@ class Reducer:
             self._native = mod.NativeReducer(self._native_ctx, engine.comm.function_table(), engine.world_size,
                                              engine._stream_ptr, engine.max_ctas, self.params)
             self._native.configure(self._native_buckets())
+            self._hook_stream = self._current_stream()
         else:
             self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
 
@@ -418,6 +419,23 @@ class Reducer:
             out.append((b.param_indices, b.offsets_el, b.lengths_el, b.dtype_code, b.nbytes, b.arena_off, b.out_off,
                         b.algo, b.fused, views))
         return out
+
+    def _current_stream(self) -> int:
+        p = self.params[0]
+        return torch.cuda.current_stream(p.device).cuda_stream if p.is_cuda else 0
+
+    def bind_stream(self) -> None:
+        """Called at the start of every forward.  The C++ loop keeps the parameters' AccumulateGrad nodes alive
+        (its post hooks live on them), and such a node runs on the stream that was current when it was created.
+        When the forward's stream changes — eager steps on the default stream, then a CUDA-graph capture on
+        torch's capture stream — the nodes are re-created under the new stream, so the whole backward stays on one
+        stream (a node left on the legacy default stream would invalidate the capture)."""
+        if self._native is None:
+            return
+        cur = self._current_stream()
+        if cur != self._hook_stream:
+            self._native.rehook()
+            self._hook_stream = cur
 
     def abort_iteration(self) -> None:
         """Forget an iteration that was armed but will never finish (an aborted CUDA-graph capture): the next
