@@ -23,6 +23,7 @@ What this module adds around that step (none of it changes what a step computes)
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -57,12 +58,12 @@ class PendingLoss:
 
     __slots__ = ("_host", "_event")
 
-    def __init__(self, host: torch.Tensor, event: torch.cuda.Event) -> None:
-        self._host, self._event = host, event
+    def __init__(self, host, event: torch.cuda.Event) -> None:
+        self._host, self._event = host, event  # host: a 1-element numpy view of the pinned loss word
 
     def item(self) -> float:
         self._event.synchronize()
-        return float(self._host)
+        return float(self._host[0])
 
     __float__ = item
 
@@ -71,7 +72,7 @@ class _Slot:
     """One captured step together with the static buffers it reads and writes."""
 
     __slots__ = ("graph", "source", "targets", "loss", "host_pack", "dev_pack", "host_source", "host_targets",
-                 "host_loss", "done")
+                 "host_loss", "host_loss_np", "done", "src_ptr", "tgt_ptr", "src_bytes", "tgt_bytes")
 
     def __init__(self) -> None:
         self.graph = None
@@ -187,11 +188,16 @@ class TrainerCore:
         slot = slots[st["host_step"] & 1]
         st["host_step"] += 1
         slot.done.synchronize()  # the replay that last read this staging buffer (two steps ago) has finished
-        slot.host_source.copy_(source)
-        slot.host_targets.copy_(targets)
+        if source.is_contiguous() and targets.is_contiguous():
+            # plain memcpy of the loader's (pinned) batch into the staging buffer: ~1 us instead of two tensor copies
+            ctypes.memmove(slot.src_ptr, source.data_ptr(), slot.src_bytes)
+            ctypes.memmove(slot.tgt_ptr, targets.data_ptr(), slot.tgt_bytes)
+        else:
+            slot.host_source.copy_(source)
+            slot.host_targets.copy_(targets)
         slot.graph.replay()
         slot.done.record()
-        return PendingLoss(slot.host_loss, slot.done)
+        return PendingLoss(slot.host_loss_np, slot.done)
 
     # ---- capture -------------------------------------------------------------------------------------
     def _capture_step(self, prologue: Callable[[], Tuple[torch.Tensor, torch.Tensor]],
@@ -265,6 +271,9 @@ class TrainerCore:
         slot.host_source.copy_(source)
         slot.host_targets.copy_(targets)
         slot.host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+        slot.host_loss_np = slot.host_loss.numpy()
+        slot.src_ptr, slot.tgt_ptr = slot.host_source.data_ptr(), slot.host_targets.data_ptr()
+        slot.src_bytes, slot.tgt_bytes = sb, tb
         slot.done = torch.cuda.Event()
         # Small batches (the toy rows: 2.7 KB) cross PCIe inside copy KERNELS that read / write the pinned buffers
         # through their device mapping (pinned memory is device-addressable under unified addressing): a

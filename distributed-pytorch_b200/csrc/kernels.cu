@@ -851,21 +851,28 @@ fused_ll_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ 
     if (w < w_end && !timed_out) {
       uint64_t t0 = 0;
       uint32_t spins = 0;
+      // one poll round = WS independent 8-byte loads in flight at once (round 1 polled the sources one after
+      // the other: ws dependent L2 round trips, ~3 us of the 5 us this kernel took at ws = 8)
+      for (;;) {
+        uint2 r[WS];
 #pragma unroll
-      for (int q = 0; q < WS; ++q) {
-        uint2 r = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
-        while (r.y != tag && !timed_out) {
-          if ((++spins & 255u) == 0) {
-            const uint64_t now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > ctl.timeout_ns) {
-              raise_timeout(pt, ctl, q);
-              timed_out = 1;
-            }
-          }
-          r = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
+        for (int q = 0; q < WS; ++q) r[q] = ld_ll(mine + static_cast<uint64_t>(q) * nwords + w);
+        int missing = -1;
+#pragma unroll
+        for (int q = 0; q < WS; ++q) {
+          val[k][q] = r[q].x;
+          if (r[q].y != tag) missing = q;
         }
-        val[k][q] = r.x;
+        if (missing < 0) break;
+        if ((++spins & 255u) == 0) {
+          const uint64_t now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > ctl.timeout_ns) {
+            raise_timeout(pt, ctl, missing);
+            timed_out = 1;
+            break;
+          }
+        }
       }
     }
   }
