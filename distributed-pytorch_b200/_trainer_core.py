@@ -14,9 +14,13 @@ What this module adds around that step (none of it changes what a step computes)
   captured (data-dependent control flow, a non-capturable optimizer) falls back to eager for good.  Capture works
   because the allreduce kernels keep their barrier generation in device memory (csrc/kernels.cu).
 * **a pipelined host path** — batches that arrive as HOST tensors (the reference's ``DataLoader(pin_memory=True)``,
-  ref:multigpu.py:72-79) go through two alternating graphs that START with the host->device copy of their own
-  pinned staging buffer and END with the device->host copy of the loss: batch i+1 is staged while step i runs, the
-  loss of step i is read when step i+1 has been queued (``PendingLoss``).
+  ref:multigpu.py:72-79) go through two alternating graphs, each on its OWN stream, that START with the
+  host->device copy of their own pinned staging buffer and END with the device->host copy of the loss.  Inside the
+  graphs the training step of graph k waits for an external event graph k-1 records after ITS step, so the step
+  chain is strictly ordered while the H2D copy of batch i+1 and the loss D2H of step i-1 run under the compute of
+  step i (measured: 28.7 us per step with copies and step serialised in one stream, 18 us for the step alone).  The
+  loss of step i is read when step i+1 has been queued (``PendingLoss``).  ``B200DDP_HOST_PIPELINE=serial`` keeps
+  both graphs on one stream.
 * **a device-resident shard**  — ``B200DDP_RESIDENT=1``: the rank's ``DistributedSampler`` shard of
   ``MyTrainDataset`` is moved to HBM once and the captured step gathers its batch by a device-side cursor, so a
   step is exactly one graph launch and no per-batch ``source.to(gpu_id)`` (ref:multigpu.py:48-50).
@@ -72,11 +76,15 @@ class _Slot:
     """One captured step together with the static buffers it reads and writes."""
 
     __slots__ = ("graph", "source", "targets", "loss", "host_pack", "dev_pack", "host_source", "host_targets",
-                 "host_loss", "host_loss_np", "done", "src_ptr", "tgt_ptr", "src_bytes", "tgt_bytes")
+                 "host_loss", "host_loss_np", "done", "src_ptr", "tgt_ptr", "src_bytes", "tgt_bytes", "stream", "events",
+                 "aliases", "raw")
 
     def __init__(self) -> None:
         self.graph = None
         self.done = None
+        self.stream = None  # host pipeline, overlap mode: the stream this slot's graph is captured and replayed on
+        self.raw = None  # (launch function, cudaGraphExec_t, cudaStream_t, cudaEvent_t) when launched through the C ABI
+
 
 
 def _signature(source: torch.Tensor, targets: torch.Tensor):
@@ -167,14 +175,26 @@ class TrainerCore:
         if st["sig"] != sig:
             if st["slots"]:
                 # a batch shaped unlike the captured one (the partial batch that ends a shard): eager this once
+                self._join_host_pipeline()
                 return self._eager_any(source, targets)
             st["sig"], st["eager_run"] = sig, 0
         kind = "dev" if source.is_cuda else "host"
+        if kind != "host":
+            self._join_host_pipeline()
         if kind not in st["slots"]:
             # eager steps first: GRAPH_AFTER of them in auto mode, and never fewer than two (the Reducer's one-time
             # bucket rebuild happens at the second forward and must precede capture)
-            if st["eager_run"] < (self.GRAPH_AFTER if st["mode"] == "auto" else 2):
+            need = self.GRAPH_AFTER if st["mode"] == "auto" else 2
+            if st["eager_run"] < need:
                 st["eager_run"] += 1
+                if "rng_free" not in st and torch.cuda.is_available():
+                    # does the step consume random numbers (dropout)?  torch's replay() advances the captured
+                    # generators' offsets; only a step that uses none may be launched through the raw handle
+                    dev = self._device()
+                    before = torch.cuda.get_rng_state(dev)
+                    out = self._eager_any(source, targets)
+                    st["rng_free"] = bool(torch.equal(before, torch.cuda.get_rng_state(dev)))
+                    return out
                 return self._eager_any(source, targets)
             if not self._try_capture(kind, source, targets):
                 return self._eager_any(source, targets)
@@ -187,6 +207,14 @@ class TrainerCore:
         slots = st["slots"]["host"]
         slot = slots[st["host_step"] & 1]
         st["host_step"] += 1
+        if slot.stream is not None:
+            if not st.get("in_host_pipeline"):
+                # entering the two-stream pipeline: both streams start after everything queued so far
+                cur = torch.cuda.current_stream(slot.dev_pack.device)
+                for s in slots:
+                    s.stream.wait_stream(cur)
+                st["in_host_pipeline"] = True
+            return self._host_step_overlapped(slot, source, targets)
         slot.done.synchronize()  # the replay that last read this staging buffer (two steps ago) has finished
         if source.is_contiguous() and targets.is_contiguous():
             # plain memcpy of the loader's (pinned) batch into the staging buffer: ~1 us instead of two tensor copies
@@ -199,9 +227,43 @@ class TrainerCore:
         slot.done.record()
         return PendingLoss(slot.host_loss_np, slot.done)
 
+    def _host_step_overlapped(self, slot: "_Slot", source: torch.Tensor, targets: torch.Tensor) -> PendingLoss:
+        slot.done.synchronize()  # this slot's previous replay (two steps ago) has released the staging buffer
+        if source.is_contiguous() and targets.is_contiguous():
+            ctypes.memmove(slot.src_ptr, source.data_ptr(), slot.src_bytes)
+            ctypes.memmove(slot.tgt_ptr, targets.data_ptr(), slot.tgt_bytes)
+        else:
+            slot.host_source.copy_(source)
+            slot.host_targets.copy_(targets)
+        raw = slot.raw
+        if raw is not None:
+            # cudaGraphLaunch + cudaEventRecord on the slot's stream in one C call (b200ddp_launch_graph): ~3 us of
+            # host time instead of ~18 us for `with stream: replay(); record()`, which made this path host-bound
+            rc = raw[0](raw[1], raw[2], raw[3])
+            if rc:
+                from . import _lib
+
+                _lib.check(rc, None, "launch_graph")
+        else:
+            with torch.cuda.stream(slot.stream):
+                slot.graph.replay()
+                slot.done.record()
+        return PendingLoss(slot.host_loss_np, slot.done)
+
+    def _join_host_pipeline(self) -> None:
+        """Leaving the two-stream host pipeline (an eager step, another replay kind, a checkpoint): the current
+        stream continues after both pipeline streams."""
+        st = self._state()
+        if st.get("in_host_pipeline"):
+            slots = st["slots"].get("host") or []
+            for s in slots:
+                if s.stream is not None:
+                    torch.cuda.current_stream(s.dev_pack.device).wait_stream(s.stream)
+            st["in_host_pipeline"] = False
+
     # ---- capture -------------------------------------------------------------------------------------
     def _capture_step(self, prologue: Callable[[], Tuple[torch.Tensor, torch.Tensor]],
-                      epilogue: Optional[Callable[[torch.Tensor], None]] = None):
+                      epilogue: Optional[Callable[[torch.Tensor], None]] = None, stream=None):
         """Capture prologue -> forward -> loss -> backward (with our bucket kernels) -> optimizer step -> epilogue.
         All ranks must call this collectively: the captured allreduce kernels synchronise across ranks."""
         dev = self._device()
@@ -210,7 +272,7 @@ class TrainerCore:
         n0 = comm.launch_count if comm is not None else 0
         self.optimizer.zero_grad(set_to_none=True)  # gradients are (re)created inside the graph's pool
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with (torch.cuda.graph(graph) if stream is None else torch.cuda.graph(graph, stream=stream)):
             source, targets = prologue()
             loss = self.loss_fn(self.model(source), targets)
             loss.backward()
@@ -227,7 +289,23 @@ class TrainerCore:
             if kind == "dev":
                 st["slots"]["dev"] = self._capture_dev(source, targets)
             else:
-                st["slots"]["host"] = [self._capture_host(source, targets) for _ in range(2)]
+                how = os.environ.get("B200DDP_HOST_PIPELINE", "overlap").lower()
+                if how not in ("overlap", "serial"):
+                    raise ValueError(f"B200DDP_HOST_PIPELINE must be overlap or serial (got {how!r})")
+                if how == "overlap":
+                    dev = self._device()
+                    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+                    # external events become event-record / event-wait NODES of the graphs: the step of graph k
+                    # waits for the step of graph k-1 wherever the two replays run
+                    stepped = [torch.cuda.Event(external=True) for _ in range(2)]
+                    cur = torch.cuda.current_stream(dev)
+                    for ev in stepped:
+                        ev.record(cur)
+                    st["slots"]["host"] = [self._capture_host(source, targets, stream=streams[k],
+                                                              wait_for=stepped[k ^ 1], signal=stepped[k])
+                                           for k in range(2)]
+                else:
+                    st["slots"]["host"] = [self._capture_host(source, targets) for _ in range(2)]
             if _truthy(os.environ.get("B200DDP_VERBOSE")):
                 print(f"[GPU{getattr(self, 'gpu_id', '?')}] training step captured into a CUDA graph (kind={kind}, "
                       f"b200ddp kernels per replay={self.graph_kernel_launches})", flush=True)
@@ -254,9 +332,12 @@ class TrainerCore:
         slot.graph, slot.loss = self._capture_step(lambda: (slot.source, slot.targets))
         return slot
 
-    def _capture_host(self, source: torch.Tensor, targets: torch.Tensor) -> _Slot:
+    def _capture_host(self, source: torch.Tensor, targets: torch.Tensor, stream=None, wait_for=None,
+                      signal=None) -> _Slot:
         """A step that begins with the H2D copy of its own pinned staging buffer (source and targets packed into
-        one transfer) and ends with the D2H copy of the loss."""
+        one transfer) and ends with the D2H copy of the loss.  Overlap mode (``stream`` given): captured on its own
+        stream; between the H2D copy and the step the graph waits for ``wait_for`` (the other graph's step), after
+        the optimizer step it records ``signal`` — only then comes the loss D2H, off the step chain."""
         dev = self._device()
         slot = _Slot()
         sb = source.numel() * source.element_size()
@@ -280,29 +361,50 @@ class TrainerCore:
         # copy-engine memcpy node costs ~7 us of graph time per transfer at this size, a kernel node ~2 us.  Large
         # batches (ResNet-50: 19 MB) keep the copy engine.  B200DDP_STAGE=memcpy|kernel forces one.
         how = os.environ.get("B200DDP_STAGE", "auto").lower()
-        mapped = how == "kernel" or (how != "memcpy" and slot.host_pack.numel() <= (64 << 10))
+        # overlap mode keeps the copy engine for every size: the copies are off the step chain there, and a
+        # copy-engine transfer runs beside the step's kernels instead of taking an SM
+        mapped = how == "kernel" or (how != "memcpy" and stream is None and slot.host_pack.numel() <= (64 << 10))
+        slot.stream = stream
+        slot.events = (wait_for, signal)  # the graph's event nodes refer to them: they live as long as the graph
         src_alias = loss_alias = None
         if mapped:
             from .comm import _CudaArray
 
             src_alias = torch.as_tensor(_CudaArray(slot.host_pack.data_ptr(), slot.host_pack.numel()), device=dev)
             loss_alias = torch.as_tensor(_CudaArray(slot.host_loss.data_ptr(), 4), device=dev).view(torch.float32)
+        slot.aliases = (src_alias, loss_alias)
 
         def prologue():
             if mapped:
                 slot.dev_pack.copy_(src_alias)  # H2D: a kernel reading the pinned staging buffer over PCIe
             else:
                 slot.dev_pack.copy_(slot.host_pack, non_blocking=True)  # H2D: copy-engine memcpy node
+            if wait_for is not None:
+                torch.cuda.current_stream(dev).wait_event(wait_for)  # event-wait node: the previous step is done
             return slot.source, slot.targets
 
         def epilogue(loss: torch.Tensor) -> None:
+            if signal is not None:
+                signal.record(torch.cuda.current_stream(dev))  # event-record node: this step is done
             if mapped:
                 loss_alias.copy_(loss.float().reshape(1))  # D2H: a 4-byte store into pinned host memory
             else:
                 slot.host_loss.copy_(loss.float().reshape(1), non_blocking=True)
 
-        slot.graph, slot.loss = self._capture_step(prologue, epilogue)
-        slot.done.record()
+        slot.graph, slot.loss = self._capture_step(prologue, epilogue, stream=stream)
+        if stream is not None:
+            slot.done.record(stream)
+            if (self._state().get("rng_free") and hasattr(slot.graph, "raw_cuda_graph_exec")
+                    and os.environ.get("B200DDP_RAW_LAUNCH", "1") not in ("0", "false", "no")):
+                from . import _lib
+
+                try:
+                    slot.raw = (_lib.load().b200ddp_launch_graph, int(slot.graph.raw_cuda_graph_exec()),
+                                int(stream.cuda_stream), int(slot.done.cuda_event))
+                except (TypeError, ValueError, RuntimeError):
+                    slot.raw = None  # this torch does not hand out the handle as an integer: torch's replay() it is
+        else:
+            slot.done.record()
         return slot
 
     def enable_cuda_graph(self, source: torch.Tensor, targets: torch.Tensor, warmup: int = 3) -> None:
@@ -312,6 +414,7 @@ class TrainerCore:
         st = self._state()
         if "dev" in st["slots"]:
             return
+        self._join_host_pipeline()
         dev = source.device
         src, tgt = source.clone(), targets.clone()
         need = max(2, warmup) if st["eager_run"] < 2 else warmup
@@ -337,6 +440,7 @@ class TrainerCore:
         st = self._state()
         if st["resident"] is not None:
             return True
+        self._join_host_pipeline()
         if loader is None:
             data = self.train_data
             ds = getattr(data, "dataset", None)
@@ -401,11 +505,13 @@ class TrainerCore:
 
     def _run_resident_step(self) -> torch.Tensor:
         """One step on the next resident batch: a single graph launch."""
+        self._join_host_pipeline()
         res = self._state()["resident"]
         res["graph"].replay()
         return res["loss"]
 
     def _run_resident_epoch(self) -> None:
+        self._join_host_pipeline()
         res = self._state()["resident"]
         res["cursor"].zero_()
         for _ in range(res["steps"]):
@@ -430,6 +536,7 @@ class TrainerCore:
 
     def _check_health(self) -> None:
         """Before a checkpoint: wait for the device and raise if any bucket kernel timed out on a peer."""
+        self._join_host_pipeline()
         check = getattr(self.model, "check_health", None)
         if check is not None:
             check(True)

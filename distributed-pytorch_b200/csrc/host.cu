@@ -1058,6 +1058,18 @@ int b200ddp_peer_read(b200ddp_ctx* c, int peer, uint64_t src_off, uint64_t dst_o
   return 0;
 }
 
+int b200ddp_launch_graph(void* graph_exec, void* stream, void* done_event) {
+  if (!graph_exec) return fail(nullptr, B200DDP_EINVAL, "launch_graph: null graph");
+  cudaError_t e = cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), static_cast<cudaStream_t>(stream));
+  if (e == cudaSuccess && done_event)
+    e = cudaEventRecord(static_cast<cudaEvent_t>(done_event), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(nullptr, B200DDP_ECUDA, "launch_graph failed: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 int b200ddp_gather_rows(const void* src, void* dst, uint64_t row_bytes, uint32_t batch_rows, uint64_t full_rows,
                         void* cursor, void* stream) {
   if (!src || !dst || !cursor) return fail(nullptr, B200DDP_EINVAL, "gather_rows: null pointer");

@@ -158,6 +158,12 @@ uint64_t b200ddp_fused_region_bytes_for(int world, uint64_t bucket_bytes);
 int b200ddp_peer_read(b200ddp_ctx* ctx, int peer, uint64_t src_off, uint64_t dst_off, uint64_t nbytes,
                       int max_ctas, void* stream);
 
+/* Launch an instantiated CUDA graph (a captured training step whose nodes include this library's kernels) on
+ * `stream` and, when `done_event` is not NULL, record it right behind: the two driver calls a replayed step costs,
+ * without the interpreter between them.  Handles are the raw cudaGraphExec_t / cudaStream_t / cudaEvent_t values.
+ * Context-free; errors via b200ddp_last_error(NULL). */
+int b200ddp_launch_graph(void* graph_exec, void* stream, void* done_event);
+
 /* Input pipeline (replaces the per-batch `source.to(gpu_id)` of ref:multigpu.py:48-50 for a shard that
  * is resident in HBM): dst[b] = src[(*cursor + b) mod full_rows] for b < batch_rows, rows of `row_bytes` (a
  * multiple of 4), then *cursor = (*cursor + batch_rows) mod full_rows.  `cursor` is a device uint64; no host state,
