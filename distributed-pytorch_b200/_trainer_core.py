@@ -499,6 +499,7 @@ class TrainerCore:
             return False
         if packed:
             self.graph_kernel_launches += 1  # gather_rows_kernel is ours too (it has no context to count it)
+        res["launches_per_replay"] = self.graph_kernel_launches
         res["cursor"].zero_()
         st["resident"] = res
         return True

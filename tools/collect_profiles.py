@@ -1,0 +1,107 @@
+"""Turn the round-2 gpurun_out/ artefacts into the committed evidence under profiles/ (summaries only)."""
+import collections, csv, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+def last_json(path):
+    try:
+        lines = [l for l in open(path).read().splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else None
+    except OSError:
+        return None
+
+# ---- bench lines -------------------------------------------------------------------------------------------
+runs = [("toy N=1 (driver-style: --steps 20 --warmup 5)", "r25_bench_n1.json"),
+        ("toy N=1 (same box as the N=2 line)", "r22_bench_n1.json"),
+        ("toy N=2 (torchrun)", "r22_bench_n2.json"),
+        ("toy N=4 (torchrun)", "r26_bench_n4.json"),
+        ("toy N=8 (torchrun)", "r23_bench_n8.json"),
+        ("toy N=8 (torchrun, final kernels)", "r27_bench_n8.json"),
+        ("resnet50 N=8 --views (gradient_as_bucket_view)", "r23_bench_resnet_views_n8.json"),
+        ("gpt2m bf16 N=8", "r23_bench_gpt2m_n8.json"),
+        ("COMPARATOR --impl nccl toy N=2", "r22_nccl_n2.json")]
+with open(os.path.join(P, "r02_bench_lines.jsonl"), "w") as f:
+    for label, name in runs:
+        d = last_json(os.path.join(G, name))
+        if d is not None:
+            d["_run"] = label
+            d["_file"] = name
+            f.write(json.dumps(d) + "\n")
+for src, dst in (("r23_cap_sweep_n8.jsonl", "r02_cap_sweep_slices_ws8.jsonl"), ("r20_ab_copy.txt", "r02_copy_kernel_ab.txt"),
+                 ("r25_host_path.txt", "r02_host_path_costs.txt")):
+    try:
+        text = open(os.path.join(G, src)).read()
+        if src.endswith(".txt"):
+            text = "\n".join(l for l in text.splitlines() if "Warning" not in l and "warn" not in l and l.strip())
+        open(os.path.join(P, dst), "w").write(text + "\n")
+    except OSError:
+        pass
+
+# ---- ncu: copy kernels ---------------------------------------------------------------------------------------
+def ncu_raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size",
+        "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct"]
+for rep, dst in (("r24_prof_copy.ncu-rep", "r02_ncu_copy_kernels_resnet_bucket.csv"),
+                 ("r24_profile_script.ncu-rep", "r02_ncu_profile_script_resnet50_step.csv")):
+    path = os.path.join(G, rep)
+    if not os.path.exists(path):
+        continue
+    hdr, units, rows = ncu_raw(path)
+    idx = [hdr.index(w) for w in WANT if w in hdr]
+    with open(os.path.join(P, dst), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] for i in idx]); w.writerow([units[i] for i in idx])
+        for r in rows:
+            w.writerow([r[i] for i in idx])
+
+# traffic of the roofline kernel: dram read + write per launch, flatten launches of the ResNet-50 bucket
+path = os.path.join(G, "r24_prof_copy.ncu-rep")
+traffic = {}
+try:
+    traffic = json.load(open(os.path.join(P, "ncu_traffic.json")))
+except OSError:
+    pass
+if os.path.exists(path):
+    hdr, units, rows = ncu_raw(path)
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    def to_bytes(v, u):
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    fl = [to_bytes(r[ri], units[ri]) + to_bytes(r[wi], units[wi]) for r in rows if "<0, 0, 4>" in r[ki]]
+    un = [to_bytes(r[ri], units[ri]) + to_bytes(r[wi], units[wi]) for r in rows if "<0, 1, 4>" in r[ki]]
+    if fl:
+        traffic["flatten_scale[resnet50 bucket]@31502336"] = {
+            "dram_bytes_per_launch": sum(fl) / len(fl), "launches": len(fl),
+            "source": "profiles/r02_ncu_copy_kernels_resnet_bucket.csv (ncu --set full, tools/prof_kernels.py): reads = S exactly; "
+                      "the 30 MB written stay dirty in the 126 MB L2 at kernel end"}
+    if un:
+        traffic["unflatten[resnet50 bucket]@31502336"] = {"dram_bytes_per_launch": sum(un) / len(un), "launches": len(un)}
+    json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+
+# ---- launch list of the replayed toy step ----------------------------------------------------------------
+path = os.path.join(G, "r24_launches_bench.csv")
+if os.path.exists(path):
+    rows = list(csv.reader(open(path)))
+    for i, r in enumerate(rows):
+        if "Kernel Name" in r:
+            hdr, start = r, i + 1
+            break
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[start:]:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", "")) / (1000 if r[ui] == "ns" else 1)
+        a = agg.setdefault(r[ki][:110], [0, 0.0]); a[0] += 1; a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(P, "r02_launches_toy_step_summary.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 python bench.py --steps 20 --warmup 5 --blocks 2 "
+                "--no-sweep --no-extra --no-nccl --no-cpu-baseline   (1x B200; cold-cache, serialised: compare SHARES)\n")
+        f.write(f"{sum(a[0] for a in agg.values())} launches, {tot:.1f} us of kernel time\n")
+        for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{c:6d} launches {t:10.1f} us {100 * t / tot:5.1f} %  {n}\n")
+print("profiles updated:", sorted(os.listdir(P)))
