@@ -105,3 +105,84 @@ if os.path.exists(path):
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{c:6d} launches {t:10.1f} us {100 * t / tot:5.1f} %  {n}\n")
 print("profiles updated:", sorted(os.listdir(P)))
+
+# ---- r02_summary.md -------------------------------------------------------------------------------------------
+def fmt(x, nd=0):
+    return "-" if x is None else (f"{x:,.{nd}f}")
+
+lines = ["# r02 — bench.py lines collected in round 2 (gpurun, this pool's B200s; every line `--steps 20 --warmup 5`, the driver's flags)",
+         "",
+         "Full lines: `r02_bench_lines.jsonl` (`_run` names each).  Lines of different N come from different boxes of the pool.",
+         "`value` = median of 30 blocks of 20 replayed steps (CUDA events, barrier + synchronize around every block, max over ranks);",
+         "`e2e` = pinned host batch -> H2D -> step -> loss D2H every step through `Trainer._run_batch`; `eager` = `B200DDP_GRAPH=0`;",
+         "`nccl_ddp` = stock torch-DDP over NCCL, same loop, same run, same GPUs.",
+         "",
+         "| run | value (samples/s) | us/step | block min..max (ms) | e2e (samples/s) | e2e/value | eager | nccl_ddp | ResNet-50 leg (ours / e2e / nccl_ddp) |",
+         "|---|---|---|---|---|---|---|---|---|"]
+sweeps = {}
+for label, name in runs:
+    d = last_json(os.path.join(G, name))
+    if d is None or d.get("impl") != "b200":
+        continue
+    ex = d.get("extra") or {}
+    bm = d.get("block_ms") or {}
+    lines.append(f"| {label} | {fmt(d['value'])} | {d['ms_per_step'] * 1e3:.1f} | {bm.get('block_ms_min', 0):.3f}..{bm.get('block_ms_max', 0):.3f} | "
+                 f"{fmt(d['e2e']['value'])} | {d['e2e']['value'] / d['value']:.2f} | {fmt((d.get('eager') or {}).get('value'))} | "
+                 f"{fmt((d.get('nccl_ddp') or {}).get('value'))} | "
+                 + (f"{fmt(ex.get('samples_s'))} / {fmt(ex.get('e2e_samples_s'))} / {fmt((ex.get('nccl_ddp') or {}).get('value'))}" if ex else "-") + " |")
+    if d.get("bucket_sweep") and "toy" in label:
+        sweeps[d["n_gpus"]] = d
+lines += ["", "## Whole-bucket device time of the step's largest bucket (`roofline_step`: CUDA-graph replay of back-to-back `engine.reduce_bucket`)", "",
+          "| run | bucket | kernels | us per bucket | achieved | fraction |", "|---|---|---|---|---|---|"]
+for label, name in runs:
+    d = last_json(os.path.join(G, name))
+    if d is None or d.get("impl") != "b200":
+        continue
+    for tag, r in (("", d.get("roofline_step")), (" (ResNet-50 leg)", (d.get("extra") or {}).get("roofline_step"))):
+        if r and "avg_launch_ms" in r:
+            lines.append(f"| {label}{tag} | {r['bucket_bytes']:,} B, {r.get('tensors')} tensors | {r['kernel']} | {r['avg_launch_ms'] * 1e3:.2f} | "
+                         f"{r['achieved']:.1f} GB/s ({r['bound']}) | {r['frac']:.3f} |")
+for n, d in sorted(sweeps.items()):
+    if n == 1:
+        lines += ["", "## N = 1: flatten / unflatten vs bucket size (HBM roofline: measured copy peak 6551 GB/s; algorithmic bytes 2 S)", "",
+                  "| kernel | bytes | tensors | us | GB/s | fraction |", "|---|---|---|---|---|---|"]
+        for p in d["bucket_sweep"]:
+            if "achieved" in p:
+                lines.append(f"| {p['kernel']} | {p['bytes']:,} | {p.get('tensors')} | {p['ms'] * 1e3:.2f} | {p['achieved']:.0f} | {p['frac']:.3f} |")
+    else:
+        lines += ["", f"## N = {n}: allreduce bus GB/s = S * 2(ws-1)/ws / t vs bucket size (fraction of the nominal 900 GB/s per direction; `*` = AUTO's choice)", ""]
+        sizes = sorted({p["bytes"] for p in d["bucket_sweep"]})
+        kernels = []
+        for p in d["bucket_sweep"]:
+            if p["kernel"] not in kernels:
+                kernels.append(p["kernel"])
+        lines.append("| kernel | " + " | ".join(f"{s / 2**20:g} MiB" for s in sizes) + " |")
+        lines.append("|---|" + "---|" * len(sizes))
+        for k in kernels:
+            row = []
+            for s in sizes:
+                m = [p for p in d["bucket_sweep"] if p["kernel"] == k and p["bytes"] == s]
+                row.append("" if not m else f"{m[0]['achieved']:.0f} ({m[0]['ms'] * 1e3:.0f} us){'*' if m[0].get('auto') else ''}")
+            lines.append(f"| {k} | " + " | ".join(row) + " |")
+        if d.get("parity"):
+            lines += ["", f"parity at N = {n} (max|a-b|/max|b| per buffer, max over 3 ragged sizes and ranks): "
+                      + "; ".join(f"{k}: vs NCCL {v['vs_nccl']:.2e}, vs rank-ordered fp32 sum {v['vs_ordered']:.2e}" for k, v in d["parity"]["max_rel"].items()),
+                      f"ok = {d['parity']['ok']}, P2P kernels bit-exact vs the rank-ordered sum = {d['parity']['p2p_bit_exact_vs_rank_ordered_sum']}"]
+        nv = d.get("nvlink") or {}
+        if nv.get("peer_read_gbs"):
+            lines += ["", f"NVLink at N = {n}: measured peer read {nv['peer_read_gbs']:.0f} GB/s per direction per GPU (all ranks pulling 256 MiB from their neighbour at once; nominal 900, pool guide 770)."]
+            for k, c in (nv.get("nvml_counters") or {}).items():
+                if isinstance(c, dict) and "tx_bytes_per_launch" in c:
+                    lines.append(f"NVML NVLink DATA counters, {k}, 64 MiB x {c['launches']} launches: TX {c['tx_bytes_per_launch'] / 1e6:.2f} MB, RX {c['rx_bytes_per_launch'] / 1e6:.2f} MB per launch; "
+                                 f"algorithmic {c['expected_per_direction'] / 1e6:.2f} MB per direction -> TX / expected = {c['tx_over_expected']:.5f}")
+cap = os.path.join(G, "r23_cap_sweep_n8.jsonl")
+if os.path.exists(cap):
+    lines += ["", "## BASELINE configs[2], model level: `slices` (64 x Linear(4096, 64), 64 MiB of gradients) vs bucket_cap_mb at N = 8 (`tools/cap_sweep.py`)", "",
+              "| bucket_cap_mb | buckets | ours samples/s | ms/step | stock DDP/NCCL samples/s | largest bucket: us, bus GB/s, fraction of 900 |", "|---|---|---|---|---|---|"]
+    for l in open(cap):
+        if l.startswith("{"):
+            c = json.loads(l)
+            lines.append(f"| {c['bucket_cap_mb']:g} | {c['buckets']} | {c['samples_s']:,.0f} | {c['ms_per_step']:.3f} | {c['nccl_ddp_samples_s']:,.0f} | "
+                         f"{c['largest_bucket_ms'] * 1e3:.0f} us, {c['largest_bucket_bus_gbs']:.0f}, {c['largest_bucket_frac']:.2f} |")
+open(os.path.join(P, "r02_summary.md"), "w").write("\n".join(lines) + "\n")
+print("wrote r02_summary.md")
