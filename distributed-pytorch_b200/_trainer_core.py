@@ -171,6 +171,10 @@ class TrainerCore:
         st = self._state()
         if st["mode"] == "off" or st["failed"] is not None:
             return self._eager_any(source, targets)
+        if st["slots"] and st.get("guard") != self._capture_guard():
+            # the optimizer's hyper-parameters (a learning-rate schedule) or the module's train/eval mode changed:
+            # a captured step has the old values baked in — drop it and capture again after fresh eager steps
+            self._drop_captures()
         sig = _signature(source, targets)
         if st["sig"] != sig:
             if st["slots"]:
@@ -226,6 +230,22 @@ class TrainerCore:
         slot.graph.replay()
         slot.done.record()
         return PendingLoss(slot.host_loss_np, slot.done)
+
+    def _capture_guard(self):
+        """What a captured step has baked in besides shapes: the optimizer's scalar hyper-parameters (they are
+        kernel arguments of the captured optimizer step) and the module's training flag."""
+        groups = getattr(self.optimizer, "param_groups", ())
+        return (getattr(self.model, "training", True),) + tuple(
+            (g.get("lr"), g.get("momentum"), g.get("weight_decay"), g.get("dampening"), g.get("nesterov")) for g in groups)
+
+    def _drop_captures(self) -> None:
+        self._join_host_pipeline()
+        dev = self._device()
+        torch.cuda.synchronize(dev)
+        st = self._state()
+        st["slots"].clear()
+        st["resident"] = None
+        st["sig"], st["eager_run"], st["host_step"] = None, 0, 0
 
     def _host_step_overlapped(self, slot: "_Slot", source: torch.Tensor, targets: torch.Tensor) -> PendingLoss:
         slot.done.synchronize()  # this slot's previous replay (two steps ago) has released the staging buffer
@@ -306,6 +326,7 @@ class TrainerCore:
                                            for k in range(2)]
                 else:
                     st["slots"]["host"] = [self._capture_host(source, targets) for _ in range(2)]
+            st["guard"] = self._capture_guard()
             if _truthy(os.environ.get("B200DDP_VERBOSE")):
                 print(f"[GPU{getattr(self, 'gpu_id', '?')}] training step captured into a CUDA graph (kind={kind}, "
                       f"b200ddp kernels per replay={self.graph_kernel_launches})", flush=True)
@@ -428,6 +449,7 @@ class TrainerCore:
         st["failed"] = None
         st["sig"] = _signature(source, targets)
         st["slots"]["dev"] = self._capture_dev(source, targets)
+        st["guard"] = self._capture_guard()
 
     # ---- device-resident shard -----------------------------------------------------------
     def enable_resident_shard(self, loader=None) -> bool:
@@ -500,6 +522,8 @@ class TrainerCore:
         if packed:
             self.graph_kernel_launches += 1  # gather_rows_kernel is ours too (it has no context to count it)
         res["launches_per_replay"] = self.graph_kernel_launches
+        if not st["slots"]:
+            st["guard"] = self._capture_guard()
         res["cursor"].zero_()
         st["resident"] = res
         return True

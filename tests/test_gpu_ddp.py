@@ -704,3 +704,39 @@ def test_loopback_ws2_gpt2_shaped_bf16_step():
     print(f"gpt2-shaped bf16 loop-back ws=2: worst rel vs fp32-accumulated average = {worst:.3e}")
     for d in ddps:
         d.shutdown()
+
+
+def test_replayed_step_follows_a_learning_rate_change(pg1, monkeypatch):
+    """A captured optimizer step has its scalar hyper-parameters baked in as kernel arguments: when the learning rate
+    (a scheduler) or the module's train/eval mode changes, the Trainer drops its captures, steps eagerly and captures
+    again — the trajectory is plain training's."""
+    from b200ddp import multigpu, utils
+
+    monkeypatch.delenv("B200DDP_GRAPH", raising=False)
+    torch.manual_seed(0)
+    ds = utils.MyTrainDataset(32 * 16, seed=31)
+    model = torch.nn.Linear(20, 1)
+    plain = copy.deepcopy(model).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    popt = torch.optim.SGD(plain.parameters(), lr=1e-2)
+    multigpu.Trainer.loss_fn = staticmethod(torch.nn.MSELoss())
+    try:
+        trainer = multigpu.Trainer(model, [], opt, 0, save_every=10**9)
+        xs, ys = ds.x.cuda(), ds.y.cuda()
+        batches = [(xs[i:i + 32], ys[i:i + 32]) for i in range(0, len(ds), 32)]
+        for i, (x, y) in enumerate(batches):
+            if i == 8:
+                for o in (opt, popt):
+                    o.param_groups[0]["lr"] = 0.5  # what a scheduler's step() does
+                assert trainer._state()["slots"].get("dev") is not None
+            trainer._run_batch(x, y)
+            if i == 8:
+                assert not trainer._state()["slots"], "captures with the old learning rate must be dropped"
+        assert trainer._state()["slots"].get("dev") is not None  # captured again after three eager steps
+        torch.cuda.synchronize()
+        _plain_steps(plain, popt.__class__(plain.parameters(), lr=1e-2), batches[:8])
+        _plain_steps(plain, torch.optim.SGD(plain.parameters(), lr=0.5), batches[8:])
+        for p, q in zip(trainer.model.module.parameters(), plain.parameters()):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    finally:
+        multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
