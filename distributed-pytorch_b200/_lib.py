@@ -45,7 +45,7 @@ SYMBOLS = [
     ("b200ddp_fused_region_bytes_for", _u64, [_i, _u64]),
     ("b200ddp_peer_read", _i, [_vp, _i, _u64, _u64, _u64, _i, _vp]),
     ("b200ddp_launch_graph", _i, [_vp, _vp, _vp]),
-    ("b200ddp_gather_rows", _i, [_vp, _vp, _u64, C.c_uint32, _u64, _vp, _vp]),
+    ("b200ddp_gather_rows", _i, [_vp, _vp, _vp, _u64, _u64, C.c_uint32, _u64, _vp, _vp]),
     ("b200ddp_clear", _i, [_vp, _u64, _u64, _vp]),
     ("b200ddp_broadcast", _i, [_vp, _u64, _u64, _i, _i, _vp]),
     ("b200ddp_barrier", _i, [_vp, _vp]),

@@ -491,14 +491,15 @@ class TrainerCore:
             lib = _lib.load()
             fx = x.shape[1]
             res["xy"] = torch.cat([x[:full], y[:full]], dim=1).contiguous()
-            res["batch"] = torch.empty(bsz, res["xy"].shape[1], dtype=x.dtype, device=dev)
+            res["bx"] = torch.empty(bsz, fx, dtype=x.dtype, device=dev)
+            res["by"] = torch.empty(bsz, y.shape[1], dtype=y.dtype, device=dev)
 
             def prologue():
-                rc = lib.b200ddp_gather_rows(res["xy"].data_ptr(), res["batch"].data_ptr(),
-                                             res["xy"].shape[1] * 4, bsz, full, res["cursor"].data_ptr(),
+                rc = lib.b200ddp_gather_rows(res["xy"].data_ptr(), res["bx"].data_ptr(), res["by"].data_ptr(),
+                                             res["xy"].shape[1] * 4, fx * 4, bsz, full, res["cursor"].data_ptr(),
                                              torch.cuda.current_stream(dev).cuda_stream)
                 _lib.check(rc, None, "gather_rows")
-                return res["batch"][:, :fx], res["batch"][:, fx:]
+                return res["bx"], res["by"]
 
             epilogue = None
         else:

@@ -1070,14 +1070,18 @@ int b200ddp_launch_graph(void* graph_exec, void* stream, void* done_event) {
   return 0;
 }
 
-int b200ddp_gather_rows(const void* src, void* dst, uint64_t row_bytes, uint32_t batch_rows, uint64_t full_rows,
-                        void* cursor, void* stream) {
-  if (!src || !dst || !cursor) return fail(nullptr, B200DDP_EINVAL, "gather_rows: null pointer");
-  if (row_bytes == 0 || (row_bytes & 3) || batch_rows == 0 || full_rows == 0 || row_bytes * batch_rows > (64u << 20) ||
-      (reinterpret_cast<uint64_t>(src) & 3) || (reinterpret_cast<uint64_t>(dst) & 3) ||
+int b200ddp_gather_rows(const void* src, void* dst, void* dst2, uint64_t row_bytes, uint64_t split_bytes,
+                        uint32_t batch_rows, uint64_t full_rows, void* cursor, void* stream) {
+  if (!src || !dst || !cursor || (split_bytes != 0 && !dst2))
+    return fail(nullptr, B200DDP_EINVAL, "gather_rows: null pointer");
+  if (row_bytes == 0 || (row_bytes & 3) || (split_bytes & 3) || split_bytes >= row_bytes || batch_rows == 0 ||
+      full_rows == 0 || row_bytes * batch_rows > (64u << 20) || (reinterpret_cast<uint64_t>(src) & 3) ||
+      (reinterpret_cast<uint64_t>(dst) & 3) || (reinterpret_cast<uint64_t>(dst2) & 3) ||
       (reinterpret_cast<uint64_t>(cursor) & 7))
-    return fail(nullptr, B200DDP_EINVAL, "gather_rows: rows must be whole 4-byte words, batch <= 64 MiB, aligned pointers");
-  cudaError_t e = launch_gather_rows(src, dst, static_cast<uint32_t>(row_bytes / 4), batch_rows, full_rows, cursor,
+    return fail(nullptr, B200DDP_EINVAL,
+                "gather_rows: rows and the split must be whole 4-byte words (split < row), batch <= 64 MiB, aligned pointers");
+  cudaError_t e = launch_gather_rows(src, dst, dst2, static_cast<uint32_t>(row_bytes / 4),
+                                     static_cast<uint32_t>(split_bytes / 4), batch_rows, full_rows, cursor,
                                      static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) {
     (void)cudaGetLastError();

@@ -77,8 +77,8 @@ cudaError_t launch_broadcast(const PeerTable& pt, const Ctl& ctl, uint64_t off, 
                              int max_ctas, cudaStream_t s);
 cudaError_t launch_barrier(const PeerTable& pt, const Ctl& ctl, cudaStream_t s);
 cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, int max_ctas, cudaStream_t s);
-cudaError_t launch_gather_rows(const void* src, void* dst, uint32_t row_words, uint32_t batch_rows, uint64_t full_rows,
-                               void* cursor, cudaStream_t s);
+cudaError_t launch_gather_rows(const void* src, void* dst, void* dst2, uint32_t row_words, uint32_t split_words,
+                               uint32_t batch_rows, uint64_t full_rows, void* cursor, cudaStream_t s);
 cudaError_t prepare_kernels(int world);  // dynamic-smem opt-in + eager load of every kernel of this world size
 
 }  // namespace b200ddp

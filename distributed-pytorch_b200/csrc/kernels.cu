@@ -419,15 +419,25 @@ __global__ void __launch_bounds__(512) local_copy_kernel(uint4* __restrict__ dst
 // cursor = (cursor + batch_rows) mod full_rows.  One launch, no host state: a captured training step replays it.
 // Single CTA: every thread reads the cursor before the barrier, thread 0 advances it after.
 // ---------------------------------------------------------------------------------------------------
+// split_words > 0: the first split_words words of every row go to dst as a dense [batch, split_words] block, the rest
+// to dst2 as a dense [batch, row_words - split_words] block (source and targets land contiguous, no strided views).
 __global__ void __launch_bounds__(256) gather_rows_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
-                                                          uint32_t row_words, uint32_t batch_rows, uint64_t full_rows,
+                                                          uint32_t* __restrict__ dst2, uint32_t row_words,
+                                                          uint32_t split_words, uint32_t batch_rows, uint64_t full_rows,
                                                           unsigned long long* cursor) {
   const uint64_t cur = *reinterpret_cast<volatile unsigned long long*>(cursor) % full_rows;
   __syncthreads();
   const uint32_t total = batch_rows * row_words;
+  const uint32_t rest = row_words - split_words;
   for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
     const uint32_t b = i / row_words, k = i - b * row_words;
-    dst[i] = src[((cur + b) % full_rows) * row_words + k];
+    const uint32_t v = src[((cur + b) % full_rows) * row_words + k];
+    if (split_words == 0)
+      dst[i] = v;
+    else if (k < split_words)
+      dst[b * split_words + k] = v;
+    else
+      dst2[b * rest + (k - split_words)] = v;
   }
   if (threadIdx.x == 0) *cursor = (cur + batch_rows) % full_rows;
 }
@@ -1029,10 +1039,11 @@ cudaError_t launch_local_copy(void* dst, const void* src, uint64_t nvec, int max
   return cudaGetLastError();
 }
 
-cudaError_t launch_gather_rows(const void* src, void* dst, uint32_t row_words, uint32_t batch_rows, uint64_t full_rows,
-                               void* cursor, cudaStream_t s) {
-  gather_rows_kernel<<<1, 256, 0, s>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), row_words,
-                                       batch_rows, full_rows, static_cast<unsigned long long*>(cursor));
+cudaError_t launch_gather_rows(const void* src, void* dst, void* dst2, uint32_t row_words, uint32_t split_words,
+                               uint32_t batch_rows, uint64_t full_rows, void* cursor, cudaStream_t s) {
+  gather_rows_kernel<<<1, 256, 0, s>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst),
+                                       static_cast<uint32_t*>(dst2), row_words, split_words, batch_rows, full_rows,
+                                       static_cast<unsigned long long*>(cursor));
   return cudaGetLastError();
 }
 

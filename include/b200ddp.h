@@ -166,10 +166,12 @@ int b200ddp_launch_graph(void* graph_exec, void* stream, void* done_event);
 
 /* Input pipeline (replaces the per-batch `source.to(gpu_id)` of ref:multigpu.py:48-50 for a shard that
  * is resident in HBM): dst[b] = src[(*cursor + b) mod full_rows] for b < batch_rows, rows of `row_bytes` (a
- * multiple of 4), then *cursor = (*cursor + batch_rows) mod full_rows.  `cursor` is a device uint64; no host state,
- * so a captured training step replays it.  Context-free (no arena involved); errors via b200ddp_last_error(NULL). */
-int b200ddp_gather_rows(const void* src, void* dst, uint64_t row_bytes, uint32_t batch_rows, uint64_t full_rows,
-                        void* cursor, void* stream);
+ * multiple of 4), then *cursor = (*cursor + batch_rows) mod full_rows.  With `split_bytes` > 0 the first split_bytes
+ * of every row land in `dst` as a dense [batch_rows, split_bytes] block and the rest in `dst2` (source and targets of a
+ * packed [source | targets] shard come out as two contiguous tensors).  `cursor` is a device uint64; no host state, so
+ * a captured training step replays it.  Context-free (no arena involved); errors via b200ddp_last_error(NULL). */
+int b200ddp_gather_rows(const void* src, void* dst, void* dst2, uint64_t row_bytes, uint64_t split_bytes,
+                        uint32_t batch_rows, uint64_t full_rows, void* cursor, void* stream);
 
 /* Zero arena[off, off + nbytes) on `stream` (offset and size multiples of 16). */
 int b200ddp_clear(b200ddp_ctx* ctx, uint64_t off, uint64_t nbytes, void* stream);

@@ -294,6 +294,7 @@ def test_loopback_ws2_graph_replay_stays_in_step():
         st = t._state()
         st["mode"], st["sig"] = "on", _signature(slot.source, slot.targets)
         st["slots"]["dev"] = slot
+        st["guard"] = t._capture_guard()
     ref = copy.deepcopy(trainers[0].model.module)
     ropt = torch.optim.SGD(ref.parameters(), lr=1e-2)
     for step in range(1, 6):

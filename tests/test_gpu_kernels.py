@@ -415,3 +415,36 @@ def test_allreduce_argument_validation(world):
         c.allreduce(0, 512, 1024, _lib.F32, _lib.ALGO_TWOSHOT, 1, s)
     with pytest.raises(RuntimeError, match="multicast"):
         c.allreduce(0, 0, 1024, _lib.F32, _lib.ALGO_NVLS, 1, s)
+
+
+def test_gather_rows_follows_the_cursor_and_wraps():
+    """b200ddp_gather_rows: batch b of a resident shard = rows (cursor + i) mod full, cursor advanced by
+    the kernel itself; with a split the source and target columns land in two dense tensors."""
+    import ctypes as C
+
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(13)
+    full, width, fx, bsz = 100, 21, 20, 32
+    shard = torch.rand(full, width, generator=gen).cuda()
+    cursor = torch.zeros((), dtype=torch.int64, device="cuda")
+    whole = torch.empty(bsz, width, device="cuda")
+    bx, by = torch.empty(bsz, fx, device="cuda"), torch.empty(bsz, width - fx, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    pos = 0
+    for step in range(9):  # 9 * 32 rows: wraps around the 100-row shard twice
+        split = step % 2 == 1
+        rc = lib.b200ddp_gather_rows(shard.data_ptr(), bx.data_ptr() if split else whole.data_ptr(),
+                                     by.data_ptr() if split else None, width * 4, fx * 4 if split else 0, bsz, full,
+                                     cursor.data_ptr(), s)
+        assert rc == 0, _lib.last_error(None)
+        torch.cuda.synchronize()
+        idx = (torch.arange(bsz) + pos) % full
+        want = shard[idx.cuda()]
+        if split:
+            assert torch.equal(bx, want[:, :fx]) and torch.equal(by, want[:, fx:])
+        else:
+            assert torch.equal(whole, want)
+        pos = (pos + bsz) % full
+        assert int(cursor) == pos
+    assert lib.b200ddp_gather_rows(shard.data_ptr(), whole.data_ptr(), None, 6, 0, bsz, full, cursor.data_ptr(), s) == -1
+    assert "4-byte words" in _lib.last_error(None)
