@@ -546,6 +546,15 @@ def bucket_sweep(torch, dist, comm_factory, world, rank, dev, hbm_peak, nvl_peak
             S_slot[0] = S
             copy_points(S, tables, reps, "", {"tensors": n_t})
             del srcs, tables
+            # comparator, not ours: torch's own copy kernel (what MEASURED_PEAKS.json's hbm_gbs was measured with, at
+            # 2 GiB) on ONE contiguous tensor of the same size in the same harness — what a plain copy reaches here
+            a = [torch.rand(S // 4, device=dev) for _ in range(reps)]
+            b = [torch.empty(S // 4, device=dev) for _ in range(reps)]
+            ms = time_graph(lambda i: b[i % reps].copy_(a[i % reps]), max(iters_for(S), reps))
+            gbs = 2 * S / (ms * 1e-3) / 1e9
+            out.append({"kernel": "torch_copy (comparator, not ours)", "bytes": S, "ms": ms, "bound": "hbm",
+                        "achieved": gbs, "peak": hbm_peak, "frac": gbs / hbm_peak, "unit": "GB/s", "tensors": 1})
+            del a, b
         try:
             reps = 10
             S, n_t, tables, keep = resnet_table(torch, TensorTable, dev, reps)
