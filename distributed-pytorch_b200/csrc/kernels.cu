@@ -323,11 +323,14 @@ multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* 
   __shared__ SmemTable s;
   // unflatten after a peer timeout: the bucket may hold a partial sum, leave the gradients alone
   if (UNFLATTEN && poison != nullptr && *reinterpret_cast<const volatile uint32_t*>(poison) != 0u) return;
-  load_table(s, tt);
+  // The tile-level lookups below are CTA-uniform and read the table straight from the kernel-parameter constant
+  // bank (uniform index: one broadcast LDC); the shared-memory copy, which per-THREAD lookups need, is only made by
+  // a CTA that meets a boundary tile.  A CTA whose tiles all lie inside aligned tensors has no prologue at all.
+  bool table_in_smem = false;
   const int n = tt.n;
-  // The grid is one co-resident wave (launch_flatten).  Default: tiles dealt round-robin (the CTAs sweep
-  // memory as a sliding window).  even_split: every CTA owns one contiguous, equal share instead — no tail,
-  // but measurably worse DRAM locality (see launch_flatten).
+  // Default grid: one CTA per tile (launch_copy_variant); with fewer CTAs than tiles the tiles are dealt
+  // round-robin (the CTAs sweep memory as a sliding window).  even_split: every CTA owns one contiguous, equal
+  // share instead — no tail, but measurably worse DRAM locality (see launch_flatten).
   const uint32_t granules = (vec_end - vec_begin + kCopyThreads - 1) / kCopyThreads;
   const uint32_t per = granules / gridDim.x, extra = granules % gridDim.x;
   const uint32_t g0 = blockIdx.x * per + min(blockIdx.x, extra);
@@ -338,15 +341,19 @@ multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* 
   uint4* bvec = reinterpret_cast<uint4*>(bucket);
   for (uint32_t v0 = r0; v0 < r1; v0 += stride) {
     const uint32_t v1 = min(v0 + kTile, r1);
-    const int t_lo = locate(s.off, 0, n - 1, v0);
-    const int t_hi = locate(s.off, t_lo, n - 1, v1 - 1);
-    const uint64_t first = static_cast<uint64_t>(v0 - s.off[t_lo]);
-    const bool fast = (t_lo == t_hi) && ((s.ptr[t_lo] & 15) == 0) &&
-                      (static_cast<uint64_t>(v1 - s.off[t_lo]) * Vec<DT>::N <= s.len[t_lo]);
+    const int t_lo = locate(tt.off_vec, 0, n - 1, v0);
+    const int t_hi = locate(tt.off_vec, t_lo, n - 1, v1 - 1);
+    const uint64_t first = static_cast<uint64_t>(v0 - tt.off_vec[t_lo]);
+    const bool fast = (t_lo == t_hi) && ((tt.ptr[t_lo] & 15) == 0) &&
+                      (static_cast<uint64_t>(v1 - tt.off_vec[t_lo]) * Vec<DT>::N <= tt.len_el[t_lo]);
     uint4 x[UNROLL];
+    if (!fast && !table_in_smem) {  // CTA-uniform branch
+      load_table(s, tt);
+      table_in_smem = true;
+    }
     if (fast) {
       // whole tile inside one aligned tensor: straight vector copy
-      uint4* tvec = reinterpret_cast<uint4*>(s.ptr[t_lo]) + first;
+      uint4* tvec = reinterpret_cast<uint4*>(tt.ptr[t_lo]) + first;
       const uint32_t cnt = v1 - v0;
 #pragma unroll
       for (int j = 0; j < UNROLL; ++j) {
@@ -987,6 +994,13 @@ inline int clamp_grid(uint64_t want, int max_ctas, int dflt) {
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------
 namespace {
+// One CTA per 32 KiB tile (up to 64 waves of 592 CTAs; beyond that CTAs loop): measured against a single co-resident
+// wave of looping CTAs, tools/ab_copy.py on B200 (profiles/r02_copy_kernel_ab.txt): 256 MiB 6.55 vs 5.86 TB/s (1.00 vs
+// 0.89 of the measured copy peak; torch's own copy kernel: 0.98), 64 MiB 0.89 vs 0.82-0.84, <= 30 MiB equal (the
+// bucket is one or two waves either way).  The hardware CTA scheduler refills an SM as soon as a CTA's stores are
+// issued, so loads of new tiles overlap the drain of old ones — what a looping CTA serialises.  Possible because a
+// CTA whose tile lies inside one tensor has no prologue (table lookups from the constant bank, see the kernel).
+constexpr uint32_t kCopyWavesDefault = 64;
 // Vectors per thread and tile of the copy kernel (B200DDP_COPY_UNROLL = 2 | 4 | 8 forces one).  Measured on B200
 // (tools/ab_copy.py, profiles/): 4 x 16 B in flight per thread at 4 CTAs x 512 threads per SM.
 int copy_unroll() {
@@ -998,10 +1012,13 @@ int copy_unroll() {
 template <int DT, int UNROLL>
 void launch_copy_variant(const TensorTable& tt, unsigned char* b, uint32_t vec_begin, uint32_t vec_end, float scale,
                          bool unflatten, int even, const uint32_t* poison, cudaStream_t s) {
-  // one co-resident wave: 4 CTAs of 512 threads per SM up to UNROLL 4 (32 registers), 2 per SM at UNROLL 8
-  const uint32_t granules = (vec_end - vec_begin + kCopyThreads - 1) / kCopyThreads;
-  const uint32_t wave = uint32_t(kNumSMs) * (UNROLL <= 4 ? 4 : 2);
-  const int grid = static_cast<int>(granules < wave ? granules : wave);
+  // one co-resident wave: 4 CTAs of 512 threads per SM up to UNROLL 4 (32 registers), 2 per SM at UNROLL 8;
+  // B200DDP_COPY_WAVES = k launches up to k waves (k >= 64: one CTA per tile, the hardware scheduler refills SMs)
+  const uint32_t tiles = (vec_end - vec_begin + kCopyThreads * UNROLL - 1) / (kCopyThreads * UNROLL);
+  const char* we = getenv("B200DDP_COPY_WAVES");
+  const uint32_t waves = we ? static_cast<uint32_t>(atoi(we) > 0 ? atoi(we) : 1) : kCopyWavesDefault;
+  const uint32_t wave = uint32_t(kNumSMs) * (UNROLL <= 4 ? 4 : 2) * waves;
+  const int grid = static_cast<int>(tiles < wave ? (tiles ? tiles : 1) : wave);
   if (unflatten)
     multi_tensor_copy_kernel<DT, true, UNROLL>
         <<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even, poison);

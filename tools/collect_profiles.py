@@ -27,7 +27,7 @@ with open(os.path.join(P, "r02_bench_lines.jsonl"), "w") as f:
             d["_run"] = label
             d["_file"] = name
             f.write(json.dumps(d) + "\n")
-for src, dst in (("r23_cap_sweep_n8.jsonl", "r02_cap_sweep_slices_ws8.jsonl"), ("r20_ab_copy.txt", "r02_copy_kernel_ab.txt"),
+for src, dst in (("r23_cap_sweep_n8.jsonl", "r02_cap_sweep_slices_ws8.jsonl"), ("r30_ab_copy.txt", "r02_copy_kernel_ab.txt"),
                  ("r25_host_path.txt", "r02_host_path_costs.txt")):
     try:
         text = open(os.path.join(G, src)).read()
