@@ -11,12 +11,16 @@ def last_json(path):
         return None
 
 # ---- bench lines -------------------------------------------------------------------------------------------
-runs = [("toy N=1 (driver-style: --steps 20 --warmup 5)", "r25_bench_n1.json"),
+runs = [("toy N=1 (final kernels)", "r31_bench_n1.json"),
+        ("toy N=1 (earlier box, before the copy-kernel grid change)", "r25_bench_n1.json"),
         ("toy N=1 (same box as the N=2 line)", "r22_bench_n1.json"),
-        ("toy N=2 (torchrun)", "r22_bench_n2.json"),
+        ("toy N=2 (torchrun, before the host pipeline overlap)", "r22_bench_n2.json"),
+        ("toy N=2 (torchrun)", "r29_bench_n2.json"),
         ("toy N=4 (torchrun)", "r26_bench_n4.json"),
-        ("toy N=8 (torchrun)", "r23_bench_n8.json"),
-        ("toy N=8 (torchrun, final kernels)", "r27_bench_n8.json"),
+        ("toy N=8 (torchrun, before the host pipeline overlap)", "r23_bench_n8.json"),
+        ("toy N=8 (torchrun)", "r27_bench_n8.json"),
+        ("toy N=8 (torchrun, final kernels)", "r31_bench_n8.json"),
+        ("REFERENCE ARM --impl reference toy N=1 (host cores, same box as the final N=1 line)", "r31_ref_n1.json"),
         ("resnet50 N=8 --views (gradient_as_bucket_view)", "r23_bench_resnet_views_n8.json"),
         ("gpt2m bf16 N=8", "r23_bench_gpt2m_n8.json"),
         ("COMPARATOR --impl nccl toy N=2", "r22_nccl_n2.json")]
@@ -28,7 +32,7 @@ with open(os.path.join(P, "r02_bench_lines.jsonl"), "w") as f:
             d["_file"] = name
             f.write(json.dumps(d) + "\n")
 for src, dst in (("r23_cap_sweep_n8.jsonl", "r02_cap_sweep_slices_ws8.jsonl"), ("r30_ab_copy.txt", "r02_copy_kernel_ab.txt"),
-                 ("r25_host_path.txt", "r02_host_path_costs.txt")):
+                 ("r31_host_path.txt", "r02_host_path_costs.txt")):
     try:
         text = open(os.path.join(G, src)).read()
         if src.endswith(".txt"):
@@ -46,8 +50,8 @@ def ncu_raw(rep):
 WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size",
         "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct"]
-for rep, dst in (("r24_prof_copy.ncu-rep", "r02_ncu_copy_kernels_resnet_bucket.csv"),
-                 ("r24_profile_script.ncu-rep", "r02_ncu_profile_script_resnet50_step.csv")):
+for rep, dst in (("r31_prof_copy.ncu-rep", "r02_ncu_copy_kernels_resnet_bucket.csv"),
+                 ("r31_profile_script.ncu-rep", "r02_ncu_profile_script_resnet50_step.csv")):
     path = os.path.join(G, rep)
     if not os.path.exists(path):
         continue
@@ -60,7 +64,7 @@ for rep, dst in (("r24_prof_copy.ncu-rep", "r02_ncu_copy_kernels_resnet_bucket.c
             w.writerow([r[i] for i in idx])
 
 # traffic of the roofline kernel: dram read + write per launch, flatten launches of the ResNet-50 bucket
-path = os.path.join(G, "r24_prof_copy.ncu-rep")
+path = os.path.join(G, "r31_prof_copy.ncu-rep")
 traffic = {}
 try:
     traffic = json.load(open(os.path.join(P, "ncu_traffic.json")))
@@ -83,7 +87,7 @@ if os.path.exists(path):
     json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
 
 # ---- launch list of the replayed toy step ----------------------------------------------------------------
-path = os.path.join(G, "r24_launches_bench.csv")
+path = os.path.join(G, "r31_launches_bench.csv")
 if os.path.exists(path):
     rows = list(csv.reader(open(path)))
     for i, r in enumerate(rows):
@@ -104,6 +108,27 @@ if os.path.exists(path):
         f.write(f"{sum(a[0] for a in agg.values())} launches, {tot:.1f} us of kernel time\n")
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{c:6d} launches {t:10.1f} us {100 * t / tot:5.1f} %  {n}\n")
+path = os.path.join(G, "r31_smoke_launches.csv")
+if os.path.exists(path):
+    rows = list(csv.reader(open(path)))
+    for i, r in enumerate(rows):
+        if "Kernel Name" in r:
+            hdr, start = r, i + 1
+            break
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[start:]:
+        if len(r) <= vi or "b200ddp" not in r[ki]:
+            continue
+        v = float(r[vi].replace(",", "")) / (1000 if r[ui] == "ns" else 1)
+        a = agg.setdefault(r[ki][:120], [0, 0.0, 0.0]); a[0] += 1; a[1] += v; a[2] = max(a[2], v)
+    with open(os.path.join(P, "r02_smoke_launches_under_ncu.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none python -c 'import __graft_entry__ as g; g.smoke()'  (what the driver\n"
+                "runs at round end): our kernels in the launch list.  Under the profiler kernels are serialised, so smoke() detects that a 2-rank\n"
+                "loop-back barrier cannot complete (one 100 ms probe: the barrier_kernel line) and skips the loop-back part instead of spinning\n"
+                "for a minute as in round 1; without a profiler the 4-rank loop-back part runs too.\n")
+        for n, (c, t, m) in agg.items():
+            f.write(f"{c:5d} launches  total {t:12.1f} us  longest {m:12.1f} us  {n}\n")
 print("profiles updated:", sorted(os.listdir(P)))
 
 # ---- r02_summary.md -------------------------------------------------------------------------------------------
