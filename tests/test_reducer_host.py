@@ -346,3 +346,23 @@ def test_comm_hook_has_the_signature_torch_checks():
     assert list(sig.parameters) == ["state", "bucket"]
     assert sig.parameters["bucket"].annotation is dist.GradBucket
     assert sig.return_annotation == torch.futures.Future[torch.Tensor]
+
+
+def test_capture_guard_tracks_optimizer_hyperparameters_and_mode():
+    """What a captured step has baked in besides shapes (TrainerCore._capture_guard): a learning-rate change (a
+    scheduler) or model.eval() must make the Trainer drop its captures."""
+    from b200ddp._trainer_core import TrainerCore
+
+    t = TrainerCore()
+    t.model = nn.Linear(4, 1)
+    t.optimizer = torch.optim.SGD(t.model.parameters(), lr=0.1, momentum=0.9)
+    g0 = t._capture_guard()
+    assert t._capture_guard() == g0
+    t.optimizer.param_groups[0]["lr"] = 0.05
+    g1 = t._capture_guard()
+    assert g1 != g0
+    t.model.eval()
+    assert t._capture_guard() != g1
+    t.model.train()
+    t.optimizer.param_groups[0]["weight_decay"] = 1e-4
+    assert t._capture_guard() != g1
