@@ -1020,6 +1020,18 @@ def main_b200(args):
                                  "stream); the timed step's own bucket is in roofline_step"}
             if world > 1 and nvlink and nvlink.get("peer_read_gbs"):
                 roofline["frac_of_measured_peer_read"] = best["achieved"] / nvlink["peer_read_gbs"]
+            if world > 1 and nvlink:
+                # no DRAM counters for kernels that wait for a peer (ncu cannot run them): the measured quantity is
+                # the NVLink wire traffic — NVML DATA TX bytes per launch of this algorithm (64 MiB x 40 launches in
+                # this run), scaled to this bucket size
+                name = best["kernel"].replace("allreduce_", "")
+                ctr = (nvlink.get("nvml_counters") or {}).get(name)
+                if isinstance(ctr, dict) and ctr.get("tx_over_expected"):
+                    factor = (1 + 1 / world) if name == "nvls" else 2 * (world - 1) / world
+                    roofline["traffic"] = ctr["tx_over_expected"] * factor * best["bytes"]
+                    roofline["traffic_kind"] = ("NVLink bytes sent per launch and GPU (NVML DATA TX counters, measured / "
+                                                f"algorithmic = {ctr['tx_over_expected']:.5f}); wire bytes = "
+                                                + ("(1+1/ws) S" if name == "nvls" else "2(ws-1)/ws S"))
     line["roofline"] = roofline if roofline is not None else roofline_step
     if legs_failed:
         line["legs_failed"] = legs_failed

@@ -29,7 +29,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Callable, Dict, Optional, Tuple
 
 import torch
 from torch.utils.data import DataLoader, Dataset
