@@ -366,3 +366,52 @@ def test_capture_guard_tracks_optimizer_hyperparameters_and_mode():
     t.model.train()
     t.optimizer.param_groups[0]["weight_decay"] = 1e-4
     assert t._capture_guard() != g1
+
+
+def test_deferred_rebuild_moves_live_bucket_views_to_private_storage():
+    """gradient_as_bucket_view: the one-time rebuild happens at the NEXT forward; gradients that are still views of
+    the old arena layout then (no zero_grad in between: gradient accumulation) must be cloned before the arena is laid
+    out anew, otherwise the re-layout would change their meaning."""
+    class ViewEngine(RecordingEngine):
+        def __init__(self):
+            super().__init__()
+            self.grad_views = True
+            self.arena = torch.zeros(1 << 16)
+            self.slots, self.used = {}, 0
+            self.cloned_before_plan = None
+
+        def owns(self, t):
+            lo = self.arena.data_ptr()
+            return t is not None and lo <= t.data_ptr() < lo + self.arena.numel() * 4
+
+        def plan(self, buckets):
+            if self.plans:  # the re-layout: no parameter may still point into the arena
+                self.cloned_before_plan = [not self.owns(p.grad) for p in self.params]
+            super().plan(buckets)
+
+        def reduce_bucket(self, bucket, grads):
+            super().reduce_bucket(bucket, grads)
+            out = []
+            for i, g in zip(bucket.param_indices, grads):  # hand back "views of the arena", like P2PEngine does
+                if i not in self.slots:
+                    self.slots[i] = self.used
+                    self.used += (g.numel() + 15) // 16 * 16
+                v = self.arena[self.slots[i]:self.slots[i] + g.numel()].view(g.shape)
+                if v.data_ptr() != g.data_ptr():
+                    v.copy_(g)
+                out.append(v)
+            return out
+
+    eng = ViewEngine()
+    model = _mlp()
+    ddp = DDP(model, bucket_cap_mb=0.01, _engine=eng, gradient_as_bucket_view=True)
+    eng.params = list(model.parameters())
+    x = torch.randn(8, 20)
+    ddp(x).square().mean().backward()
+    assert all(eng.owns(p.grad) for p in model.parameters()) and not ddp.reducer.has_rebuilt
+    kept = [p.grad.clone() for p in model.parameters()]
+    ddp(x).square().mean().backward()  # no zero_grad: the second forward rebuilds with the views still alive
+    assert ddp.reducer.has_rebuilt and len(eng.plans) == 2
+    assert eng.cloned_before_plan == [True] * 6
+    for p, k in zip(model.parameters(), kept):
+        assert torch.allclose(p.grad, 2 * k)  # accumulated on top of the preserved values
