@@ -23,6 +23,9 @@ runs = [("toy N=1 (final kernels)", "r31_bench_n1.json"),
         ("REFERENCE ARM --impl reference toy N=1 (host cores, same box as the final N=1 line)", "r31_ref_n1.json"),
         ("resnet50 N=8 --views (gradient_as_bucket_view)", "r23_bench_resnet_views_n8.json"),
         ("gpt2m bf16 N=8", "r23_bench_gpt2m_n8.json"),
+        ("wide (configs[2], one 64 MiB bucket) N=2", "r32_bench_wide_n2.json"),
+        ("slices (configs[2]) N=1", "r32_bench_slices_n1.json"),
+        ("toy N=2 --graph off (every step eager, --steps 200)", "r32_bench_toy_eager_n2.json"),
         ("COMPARATOR --impl nccl toy N=2", "r22_nccl_n2.json")]
 with open(os.path.join(P, "r02_bench_lines.jsonl"), "w") as f:
     for label, name in runs:
