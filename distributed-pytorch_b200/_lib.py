@@ -39,6 +39,8 @@ SYMBOLS = [
     ("b200ddp_unflatten", _i, [_vp, _pp, _pu64, _pu64, _i, _i, _u64, _vp]),
     ("b200ddp_allreduce", _i, [_vp, _u64, _u64, _u64, _i, _i, _i, _f, _vp]),
     ("b200ddp_fused_bucket", _i, [_vp, _pp, _pu64, _pu64, _i, _i, _u64, _u64, _f, _vp]),
+    ("b200ddp_unflatten_sgd", _i, [_vp, _pp, _pp, _pu64, _pu64, _i, _i, _u64, _f, _vp]),
+    ("b200ddp_fused_bucket_sgd", _i, [_vp, _pp, _pp, _pu64, _pu64, _i, _i, _u64, _u64, _f, _f, _vp]),
     ("b200ddp_max_table_tensors", _i, []),
     ("b200ddp_fused_max_bytes", _u64, []),
     ("b200ddp_fused_region_bytes", _u64, [_vp, _u64]),

@@ -114,6 +114,8 @@ class TrainerCore:
         self.gpu_id, self.save_every = gpu_id, save_every
         self.train_data, self.optimizer = train_data, optimizer
         self.model = wrapped
+        if _truthy(os.environ.get("B200DDP_FUSE_SGD")) and hasattr(wrapped, "fuse_optimizer"):
+            wrapped.fuse_optimizer(optimizer)  # opt-in: the bucket kernels also apply the SGD step (ddp.py)
 
     def _state(self) -> Dict:
         st = self.__dict__.get("_graph_state")

@@ -50,15 +50,18 @@ class _CudaArray:
 class TensorTable:
     """ctypes arrays (pointers, element offsets, element counts) for one multi-tensor call."""
 
-    __slots__ = ("n", "ptrs", "offs", "lens", "key")
+    __slots__ = ("n", "ptrs", "offs", "lens", "key", "params")
 
-    def __init__(self, data_ptrs: Sequence[int], offsets_el: Sequence[int], lengths_el: Sequence[int]) -> None:
+    def __init__(self, data_ptrs: Sequence[int], offsets_el: Sequence[int], lengths_el: Sequence[int],
+                 param_ptrs: Optional[Sequence[int]] = None) -> None:
         n = len(data_ptrs)
         self.n = n
         self.ptrs = (C.c_void_p * n)(*data_ptrs)
         self.offs = (C.c_uint64 * n)(*offsets_el)
         self.lens = (C.c_uint64 * n)(*lengths_el)
         self.key = tuple(data_ptrs)
+        #: storage of the parameter each tensor is the gradient of (optimizer epilogue, opt-in)
+        self.params = None if param_ptrs is None else (C.c_void_p * n)(*param_ptrs)
 
 
 class P2PComm:
@@ -172,6 +175,19 @@ class P2PComm:
     def peer_read(self, peer: int, src_off: int, dst_off: int, nbytes: int, stream: int, max_ctas: int = 0) -> None:
         _lib.check(self._lib.b200ddp_peer_read(self._ctx, peer, src_off, dst_off, nbytes, max_ctas, stream),
                    self._ctx, "peer_read")
+
+    def unflatten_sgd(self, table: TensorTable, dtype: int, bucket_off: int, lr: float, stream: int) -> None:
+        rc = self._lib.b200ddp_unflatten_sgd(self._ctx, table.ptrs, table.params, table.offs, table.lens, table.n, dtype,
+                                             bucket_off, lr, stream)
+        if rc:
+            _lib.check(rc, self._ctx, "unflatten_sgd")
+
+    def fused_bucket_sgd(self, table: TensorTable, dtype: int, bucket_off: int, bucket_bytes: int, scale: float,
+                         lr: float, stream: int) -> None:
+        rc = self._lib.b200ddp_fused_bucket_sgd(self._ctx, table.ptrs, table.params, table.offs, table.lens, table.n,
+                                                dtype, bucket_off, bucket_bytes, scale, lr, stream)
+        if rc:
+            _lib.check(rc, self._ctx, "fused_bucket_sgd")
 
     def fused_region_bytes(self, bucket_bytes: int) -> int:
         return int(self._lib.b200ddp_fused_region_bytes(self._ctx, bucket_bytes))

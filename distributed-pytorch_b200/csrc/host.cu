@@ -622,8 +622,21 @@ int build_table(b200ddp_ctx* c, const void* const* ptrs, const uint64_t* off_el,
   return 0;
 }
 
+// parameter pointers of tensors [i0, i1) + the learning rate -> the kernels' optimizer-epilogue table
+int build_sgd(b200ddp_ctx* c, void* const* param_ptrs, int i0, int i1, int esize, float lr, SgdTable* st) {
+  if (!(lr == lr) || lr == 0.0f) return fail(c, B200DDP_EINVAL, "sgd: the learning rate must be a non-zero number");
+  for (int i = i0; i < i1; ++i) {
+    if (reinterpret_cast<uint64_t>(param_ptrs[i]) % esize)
+      return fail(c, B200DDP_EINVAL, "parameter %d: pointer not aligned to its element size", i);
+    st->ptr[i - i0] = reinterpret_cast<uint64_t>(param_ptrs[i]);  // NULL = this tensor has no parameter to update
+  }
+  st->neg_lr = -lr;
+  return 0;
+}
+
 int copy_bucket(b200ddp_ctx* c, const void* const* ptrs, const uint64_t* off_el, const uint64_t* len_el, int n,
-                int dtype, uint64_t bucket_off, float scale, bool unflatten, void* stream) {
+                int dtype, uint64_t bucket_off, float scale, bool unflatten, void* stream,
+                void* const* param_ptrs = nullptr, float lr = 0.0f) {
   int rc = check_ready(c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -645,7 +658,10 @@ int copy_bucket(b200ddp_ctx* c, const void* const* ptrs, const uint64_t* off_el,
     const uint32_t* poison = (unflatten && c->world > 1)
                                  ? reinterpret_cast<const uint32_t*>(static_cast<unsigned char*>(c->base) + kFlagBytes + kEpochBytes)
                                  : nullptr;
-    RT_CHECK(c, launch_flatten(tt, bucket, vb, ve, dtype, scale, unflatten, poison, static_cast<cudaStream_t>(stream)));
+    SgdTable st;
+    if (param_ptrs && (rc = build_sgd(c, param_ptrs, i0, i1, esize, lr, &st))) return rc;
+    RT_CHECK(c, launch_flatten(tt, bucket, vb, ve, dtype, scale, unflatten, poison, static_cast<cudaStream_t>(stream),
+                               param_ptrs ? &st : nullptr));
     c->launches++;
   }
   return 0;
@@ -930,6 +946,12 @@ int b200ddp_unflatten(b200ddp_ctx* c, void* const* grad_ptrs, const uint64_t* of
   return copy_bucket(c, grad_ptrs, off_el, len_el, n, dtype, bucket_off, 1.0f, true, stream);
 }
 
+int b200ddp_unflatten_sgd(b200ddp_ctx* c, void* const* grad_ptrs, void* const* param_ptrs, const uint64_t* off_el,
+                          const uint64_t* len_el, int n, int dtype, uint64_t bucket_off, float lr, void* stream) {
+  if (c && !param_ptrs) return fail(c, B200DDP_EINVAL, "unflatten_sgd: param_ptrs is null");
+  return copy_bucket(c, grad_ptrs, off_el, len_el, n, dtype, bucket_off, 1.0f, true, stream, param_ptrs, lr);
+}
+
 int b200ddp_pick_algo(b200ddp_ctx* c, uint64_t nbytes) {
   if (!c) return B200DDP_EINVAL;
   const int forced = env_int("B200DDP_ALGO", 0);
@@ -1003,8 +1025,30 @@ int b200ddp_allreduce(b200ddp_ctx* c, uint64_t in_off, uint64_t out_off, uint64_
   return 0;
 }
 
+namespace {
+int fused_bucket_impl(b200ddp_ctx* c, void* const* grad_ptrs, void* const* param_ptrs, const uint64_t* off_el,
+                      const uint64_t* len_el, int n, int dtype, uint64_t bucket_off, uint64_t bucket_bytes, float scale,
+                      float lr, void* stream);
+}
+
 int b200ddp_fused_bucket(b200ddp_ctx* c, void* const* grad_ptrs, const uint64_t* off_el, const uint64_t* len_el,
                          int n, int dtype, uint64_t bucket_off, uint64_t bucket_bytes, float scale, void* stream) {
+  return fused_bucket_impl(c, grad_ptrs, nullptr, off_el, len_el, n, dtype, bucket_off, bucket_bytes, scale, 0.0f, stream);
+}
+
+int b200ddp_fused_bucket_sgd(b200ddp_ctx* c, void* const* grad_ptrs, void* const* param_ptrs, const uint64_t* off_el,
+                             const uint64_t* len_el, int n, int dtype, uint64_t bucket_off, uint64_t bucket_bytes,
+                             float scale, float lr, void* stream) {
+  if (c && !param_ptrs) return fail(c, B200DDP_EINVAL, "fused_bucket_sgd: param_ptrs is null");
+  return fused_bucket_impl(c, grad_ptrs, param_ptrs, off_el, len_el, n, dtype, bucket_off, bucket_bytes, scale, lr, stream);
+}
+
+}  // extern "C"
+
+namespace {
+int fused_bucket_impl(b200ddp_ctx* c, void* const* grad_ptrs, void* const* param_ptrs, const uint64_t* off_el,
+                      const uint64_t* len_el, int n, int dtype, uint64_t bucket_off, uint64_t bucket_bytes, float scale,
+                      float lr, void* stream) {
   int rc = check_ready(c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -1021,12 +1065,17 @@ int b200ddp_fused_bucket(b200ddp_ctx* c, void* const* grad_ptrs, const uint64_t*
   rc = build_table(c, const_cast<const void* const*>(grad_ptrs), off_el, len_el, 0, n, esize, &tt, &vb, &ve);
   if (rc) return rc;
   if (uint64_t(ve) * 16 > bucket_bytes) return fail(c, B200DDP_EINVAL, "tensor table exceeds bucket_bytes");
+  SgdTable st;
+  if (param_ptrs && (rc = build_sgd(c, param_ptrs, 0, n, esize, lr, &st))) return rc;
   DeviceGuard g(c->device);
   RT_CHECK(c, launch_fused(tt, c->pt, make_ctl(c), bucket_off, static_cast<uint32_t>(bucket_bytes / 16), dtype, scale,
-                           static_cast<cudaStream_t>(stream)));
+                           static_cast<cudaStream_t>(stream), param_ptrs ? &st : nullptr));
   c->launches++;
   return 0;
 }
+}  // namespace
+
+extern "C" {
 
 int b200ddp_broadcast(b200ddp_ctx* c, uint64_t off, uint64_t nbytes, int root, int max_ctas, void* stream) {
   int rc = check_ready(c);

@@ -56,11 +56,21 @@ struct TensorTable {
   int32_t n;
 };
 
-// kernels.cu — launch wrappers.  All return cudaError_t from the launch.
+// Optional optimizer epilogue (opt-in): parameter i of the bucket's tensor table lives at ptr[i];
+// wherever a kernel writes the averaged gradient g back it also applies plain SGD, p <- fma(-lr, g, p) (what
+// torch.optim.SGD's `param.add_(grad, alpha=-lr)` computes, ref:multigpu.py:43,68).  Travels in the kernel-parameter
+// space like the tensor table; kernels are instantiated with and without it, so the default launches carry none of it.
+struct SgdTable {
+  uint64_t ptr[kMaxTableTensors];
+  float neg_lr;
+};
+
+// kernels.cu — launch wrappers.  All return cudaError_t from the launch.  `sgd` == nullptr: no optimizer epilogue.
 // `poison`: the rank's sticky timeout word (device pointer) — an unflatten launch returns without writing when
 // it is set; nullptr = no check
 cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_begin, uint32_t vec_end, int dtype,
-                           float scale, bool unflatten, const uint32_t* poison, cudaStream_t s);
+                           float scale, bool unflatten, const uint32_t* poison, cudaStream_t s,
+                           const SgdTable* sgd = nullptr);
 cudaError_t launch_oneshot(const PeerTable& pt, const Ctl& ctl, uint64_t in_off, uint64_t out_off, uint64_t nvec,
                            int dtype, int max_ctas, float scale, cudaStream_t s);
 // `scale` multiplies the reduced sum before it is written back (1.0 = none; the Reducer pre-scales in flatten
@@ -72,7 +82,7 @@ cudaError_t launch_twoshot_tma(const PeerTable& pt, const Ctl& ctl, uint64_t in_
 cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, uint64_t in_off, uint64_t out_off,
                         uint64_t nvec, int dtype, int max_ctas, float scale, cudaStream_t s);
 cudaError_t launch_fused(const TensorTable& tt, const PeerTable& pt, const Ctl& ctl, uint64_t bucket_off,
-                         uint32_t nvec, int dtype, float scale, cudaStream_t s);
+                         uint32_t nvec, int dtype, float scale, cudaStream_t s, const SgdTable* sgd = nullptr);
 cudaError_t launch_broadcast(const PeerTable& pt, const Ctl& ctl, uint64_t off, uint64_t nvec, int root,
                              int max_ctas, cudaStream_t s);
 cudaError_t launch_barrier(const PeerTable& pt, const Ctl& ctl, cudaStream_t s);

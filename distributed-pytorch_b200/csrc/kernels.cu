@@ -304,6 +304,48 @@ __device__ __forceinline__ void scatter_vec(const SmemTable& s, int t, uint32_t 
   }
 }
 
+// ---- optional optimizer epilogue (opt-in, SgdTable in internal.h) -----------------------------------------------
+struct NoSgd {};
+template <bool SGD>
+struct SgdArg {
+  using type = NoSgd;
+};
+template <>
+struct SgdArg<true> {
+  using type = SgdTable;
+};
+
+// p <- fma(neg_lr, g, p) on the elements of tensor storage `pbase` (len elements) that bucket vector element e0.. covers
+template <int DT>
+__device__ __forceinline__ void sgd_vec(uint64_t pbase, uint64_t len, uint64_t e0, const uint4& g, float neg_lr) {
+  constexpr int N = Vec<DT>::N;
+  if (pbase == 0 || e0 >= len) return;
+  const uint64_t addr = pbase + e0 * Vec<DT>::ESIZE;
+  float gf[N];
+  Vec<DT>::unpack(g, gf);
+  if (e0 + N <= len && (addr & 15) == 0) {
+    float pf[N];
+    Vec<DT>::unpack(ld_vec(reinterpret_cast<const void*>(addr)), pf);
+#pragma unroll
+    for (int i = 0; i < N; ++i) pf[i] = __fmaf_rn(neg_lr, gf[i], pf[i]);
+    st_vec(reinterpret_cast<void*>(addr), Vec<DT>::pack(pf));
+    return;
+  }
+  const int valid = static_cast<int>(min(static_cast<uint64_t>(N), len - e0));
+  if (Vec<DT>::ESIZE == 4) {
+    float* p = reinterpret_cast<float*>(addr);
+    for (int i = 0; i < valid; ++i) p[i] = __fmaf_rn(neg_lr, gf[i], p[i]);
+  } else {
+    uint16_t* p = reinterpret_cast<uint16_t*>(addr);
+    for (int i = 0; i < valid; ++i) {
+      float one[N] = {};
+      Vec<DT>::unpack(make_uint4(p[i], 0, 0, 0), one);
+      one[0] = __fmaf_rn(neg_lr, gf[i], one[0]);
+      p[i] = static_cast<uint16_t>(Vec<DT>::pack(one).x);
+    }
+  }
+}
+
 constexpr int kCopyThreads = 512;
 
 // One launch moves bucket vectors [vec_begin, vec_end) (all inside the tensors of `tt`).
@@ -314,11 +356,12 @@ constexpr int kCopyThreads = 512;
 // vector up in the shared-memory table (binary search over the <= few tensors of the tile) but keep the same
 // loads-then-stores structure, so such a tile costs one memory round trip like any other (round 1 walked it
 // one dependent vector at a time and those tiles finished last: 0.44 of the HBM roofline on ResNet-50 buckets).
-template <int DT, bool UNFLATTEN, int UNROLL>
-__global__ void __launch_bounds__(kCopyThreads, UNROLL <= 4 ? 4 : 2)
+template <int DT, bool UNFLATTEN, int UNROLL, bool SGD = false>
+__global__ void __launch_bounds__(kCopyThreads, (UNROLL <= 4 && !SGD) ? 4 : 2)
 multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* __restrict__ bucket,
                          uint32_t vec_begin, uint32_t vec_end, float scale, int even_split,
-                         const uint32_t* __restrict__ poison) {
+                         const uint32_t* __restrict__ poison, const __grid_constant__ typename SgdArg<SGD>::type sgd) {
+  static_assert(!SGD || UNFLATTEN, "the optimizer epilogue belongs to the unflatten direction");
   constexpr uint32_t kTile = kCopyThreads * UNROLL;
   __shared__ SmemTable s;
   // unflatten after a peer timeout: the bucket may hold a partial sum, leave the gradients alone
@@ -344,8 +387,9 @@ multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* 
     const int t_lo = locate(tt.off_vec, 0, n - 1, v0);
     const int t_hi = locate(tt.off_vec, t_lo, n - 1, v1 - 1);
     const uint64_t first = static_cast<uint64_t>(v0 - tt.off_vec[t_lo]);
-    const bool fast = (t_lo == t_hi) && ((tt.ptr[t_lo] & 15) == 0) &&
-                      (static_cast<uint64_t>(v1 - tt.off_vec[t_lo]) * Vec<DT>::N <= tt.len_el[t_lo]);
+    bool fast = (t_lo == t_hi) && ((tt.ptr[t_lo] & 15) == 0) &&
+                (static_cast<uint64_t>(v1 - tt.off_vec[t_lo]) * Vec<DT>::N <= tt.len_el[t_lo]);
+    if constexpr (SGD) fast = fast && ((sgd.ptr[t_lo] & 15) == 0);  // an unaligned parameter takes the general path
     uint4 x[UNROLL];
     if (!fast && !table_in_smem) {  // CTA-uniform branch
       load_table(s, tt);
@@ -370,6 +414,30 @@ multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* 
             st_vec(bvec + v0 + i, scale_vec<DT>(x[j], scale));
         }
       }
+      if constexpr (SGD) {
+        // p <- fma(-lr, g, p) on the same vectors (the parameter is laid out like its gradient)
+        if (sgd.ptr[t_lo] != 0) {
+          uint4* pvec = reinterpret_cast<uint4*>(sgd.ptr[t_lo]) + first;
+          uint4 p[UNROLL];
+#pragma unroll
+          for (int j = 0; j < UNROLL; ++j) {
+            const uint32_t i = threadIdx.x + j * kCopyThreads;
+            if (i < cnt) p[j] = ld_vec(pvec + i);
+          }
+#pragma unroll
+          for (int j = 0; j < UNROLL; ++j) {
+            const uint32_t i = threadIdx.x + j * kCopyThreads;
+            if (i < cnt) {
+              float pf[Vec<DT>::N], gf[Vec<DT>::N];
+              Vec<DT>::unpack(p[j], pf);
+              Vec<DT>::unpack(x[j], gf);
+#pragma unroll
+              for (int k = 0; k < Vec<DT>::N; ++k) pf[k] = __fmaf_rn(sgd.neg_lr, gf[k], pf[k]);
+              st_vec(pvec + i, Vec<DT>::pack(pf));
+            }
+          }
+        }
+      }
     } else if (UNFLATTEN) {
       // bucket-side loads do not depend on the tensor lookup: issue them all, search while they fly
 #pragma unroll
@@ -380,7 +448,12 @@ multi_tensor_copy_kernel(const __grid_constant__ TensorTable tt, unsigned char* 
 #pragma unroll
       for (int j = 0; j < UNROLL; ++j) {
         const uint32_t v = v0 + threadIdx.x + j * kCopyThreads;
-        if (v < v1) scatter_vec<DT>(s, locate(s.off, t_lo, t_hi, v), v, x[j]);
+        if (v < v1) {
+          const int t = locate(s.off, t_lo, t_hi, v);
+          scatter_vec<DT>(s, t, v, x[j]);
+          if constexpr (SGD)
+            sgd_vec<DT>(sgd.ptr[t], s.len[t], static_cast<uint64_t>(v - s.off[t]) * Vec<DT>::N, x[j], sgd.neg_lr);
+        }
       }
     } else {
       int t[UNROLL];
@@ -731,10 +804,11 @@ nvls_kernel(const __grid_constant__ PeerTable pt, const __grid_constant__ Ctl ct
 constexpr int kFusedThreads = 256;
 constexpr uint32_t kFusedVecPerCta = 1024;
 
-template <int DT, int WS>
+template <int DT, int WS, bool SGD = false>
 __global__ void __launch_bounds__(kFusedThreads)
 fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ PeerTable pt,
-                    const __grid_constant__ Ctl ctl, uint64_t bucket_off, uint32_t nvec, float scale) {
+                    const __grid_constant__ Ctl ctl, uint64_t bucket_off, uint32_t nvec, float scale,
+                    const __grid_constant__ typename SgdArg<SGD>::type sgd) {
   __shared__ SmemTable s;
   load_table(s, tt);
   const int n = tt.n;
@@ -747,6 +821,8 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
       const uint4 x = scale_vec<DT>(gather_vec<DT>(s, t, v), scale);
       st_vec(mine + v, x);
       scatter_vec<DT>(s, t, v, x);
+      if constexpr (SGD)
+        sgd_vec<DT>(sgd.ptr[t], s.len[t], static_cast<uint64_t>(v - s.off[t]) * Vec<DT>::N, x, sgd.neg_lr);
     }
     return;
   }
@@ -767,7 +843,10 @@ fused_bucket_kernel(const __grid_constant__ TensorTable tt, const __grid_constan
 #pragma unroll
     for (int q = 0; q < WS; ++q) x[q] = ld_vec(in[q] + v);
     const int t = locate(s.off, 0, n - 1, v);
-    scatter_vec<DT>(s, t, v, reduce_vecs<DT, WS>(x));
+    const uint4 r = reduce_vecs<DT, WS>(x);
+    scatter_vec<DT>(s, t, v, r);
+    if constexpr (SGD)
+      sgd_vec<DT>(sgd.ptr[t], s.len[t], static_cast<uint64_t>(v - s.off[t]) * Vec<DT>::N, r, sgd.neg_lr);
   }
   write_epoch(pt, ctl, e + 2);
 }
@@ -835,10 +914,40 @@ __device__ __forceinline__ void scatter_word(const SmemTable& s, int t, uint32_t
   }
 }
 
-template <int DT, int WS>
+// p <- fma(neg_lr, g, p) for the one (fp32) or two (bf16/f16) elements bucket word w of tensor t covers
+template <int DT>
+__device__ __forceinline__ void sgd_word(uint64_t pbase, const SmemTable& s, int t, uint32_t w, uint32_t bits,
+                                         float neg_lr) {
+  if (pbase == 0) return;
+  const uint32_t v = w >> 2, j = w & 3;
+  const uint64_t len = s.len[t];
+  float gf[Vec<DT>::N] = {};
+  Vec<DT>::unpack(make_uint4(bits, 0, 0, 0), gf);
+  if (Vec<DT>::ESIZE == 4) {
+    const uint64_t e = static_cast<uint64_t>(v - s.off[t]) * 4 + j;
+    if (e < len) {
+      float* p = reinterpret_cast<float*>(pbase) + e;
+      *p = __fmaf_rn(neg_lr, gf[0], *p);
+    }
+  } else {
+    const uint64_t e = static_cast<uint64_t>(v - s.off[t]) * 8 + 2 * j;
+    uint16_t* p = reinterpret_cast<uint16_t*>(pbase);
+    for (int k = 0; k < 2; ++k) {
+      if (e + k < len) {
+        float one[Vec<DT>::N] = {};
+        Vec<DT>::unpack(make_uint4(p[e + k], 0, 0, 0), one);
+        one[0] = __fmaf_rn(neg_lr, gf[k], one[0]);
+        p[e + k] = static_cast<uint16_t>(Vec<DT>::pack(one).x);
+      }
+    }
+  }
+}
+
+template <int DT, int WS, bool SGD = false>
 __global__ void __launch_bounds__(kLLThreads)
 fused_ll_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ PeerTable pt,
-                const __grid_constant__ Ctl ctl, uint64_t ll_off, uint32_t nwords, float scale) {
+                const __grid_constant__ Ctl ctl, uint64_t ll_off, uint32_t nwords, float scale,
+                const __grid_constant__ typename SgdArg<SGD>::type sgd) {
   __shared__ SmemTable s;
   if (poisoned(pt, ctl)) return;
   const uint32_t e = read_epoch(pt, ctl);  // before the barrier inside load_table: thread 0 rewrites it at the end
@@ -904,7 +1013,9 @@ fused_ll_kernel(const __grid_constant__ TensorTable tt, const __grid_constant__ 
 #pragma unroll
       for (int q = 0; q < WS; ++q) x[q] = make_uint4(val[k][q], 0, 0, 0);
       const int t = locate(s.off, 0, n - 1, w >> 2);
-      scatter_word<DT>(s, t, w, reduce_vecs<DT, WS>(x).x);
+      const uint32_t bits = reduce_vecs<DT, WS>(x).x;
+      scatter_word<DT>(s, t, w, bits);
+      if constexpr (SGD) sgd_word<DT>(sgd.ptr[t], s, t, w, bits, sgd.neg_lr);
     }
   }
   write_epoch(pt, ctl, e + 2);
@@ -1012,6 +1123,7 @@ int copy_unroll() {
 template <int DT, int UNROLL>
 void launch_copy_variant(const TensorTable& tt, unsigned char* b, uint32_t vec_begin, uint32_t vec_end, float scale,
                          bool unflatten, int even, const uint32_t* poison, cudaStream_t s) {
+  const NoSgd none{};
   // one co-resident wave: 4 CTAs of 512 threads per SM up to UNROLL 4 (32 registers), 2 per SM at UNROLL 8;
   // B200DDP_COPY_WAVES = k launches up to k waves (k >= 64: one CTA per tile, the hardware scheduler refills SMs)
   const uint32_t tiles = (vec_end - vec_begin + kCopyThreads * UNROLL - 1) / (kCopyThreads * UNROLL);
@@ -1021,17 +1133,29 @@ void launch_copy_variant(const TensorTable& tt, unsigned char* b, uint32_t vec_b
   const int grid = static_cast<int>(tiles < wave ? (tiles ? tiles : 1) : wave);
   if (unflatten)
     multi_tensor_copy_kernel<DT, true, UNROLL>
-        <<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even, poison);
+        <<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even, poison, none);
   else
     multi_tensor_copy_kernel<DT, false, UNROLL>
-        <<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even, nullptr);
+        <<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, even, nullptr, none);
 }
 }  // namespace
 
 cudaError_t launch_flatten(const TensorTable& tt, void* bucket, uint32_t vec_begin, uint32_t vec_end, int dtype,
-                           float scale, bool unflatten, const uint32_t* poison, cudaStream_t s) {
+                           float scale, bool unflatten, const uint32_t* poison, cudaStream_t s, const SgdTable* sgd) {
   if (vec_end <= vec_begin || tt.n <= 0) return cudaSuccess;
   unsigned char* b = static_cast<unsigned char*>(bucket);
+  if (sgd != nullptr) {
+    // unflatten + optimizer epilogue: one CTA per 32 KiB tile, 2 CTAs per SM (the parameter vectors double the
+    // registers in flight)
+    if (!unflatten) return cudaErrorInvalidValue;
+    const uint32_t tiles = (vec_end - vec_begin + kCopyThreads * 4 - 1) / (kCopyThreads * 4);
+    const int grid = static_cast<int>(tiles < 65535u ? tiles : 65535u);
+    B200_DISPATCH_DT(dtype, {
+      multi_tensor_copy_kernel<DT, true, 4, true>
+          <<<grid, kCopyThreads, 0, s>>>(tt, b, vec_begin, vec_end, scale, 0, poison, *sgd);
+    });
+    return cudaGetLastError();
+  }
   // Work split, A/B-measured on one box (tools/ab_copy.py): dealing tiles round-robin makes the co-resident
   // CTAs sweep memory as a sliding window and beat an even per-CTA split by 2-7 % at 16-256 MiB (25 MiB:
   // 4.88 vs 4.58 TB/s), so it is the default; B200DDP_COPY_SPLIT=even selects the other.
@@ -1122,24 +1246,46 @@ cudaError_t launch_nvls(const PeerTable& pt, const Ctl& ctl, uint64_t mc_base, u
 }
 
 cudaError_t launch_fused(const TensorTable& tt, const PeerTable& pt, const Ctl& ctl, uint64_t bucket_off,
-                         uint32_t nvec, int dtype, float scale, cudaStream_t s) {
+                         uint32_t nvec, int dtype, float scale, cudaStream_t s, const SgdTable* sgd) {
   if (nvec == 0 || tt.n <= 0) return cudaSuccess;
   const int grid = static_cast<int>((nvec + kFusedVecPerCta - 1) / kFusedVecPerCta);
   if (grid > kMaxBlocks) return cudaErrorInvalidValue;
+  const NoSgd none{};
+  if (sgd != nullptr) {  // the same three kernels with the optimizer epilogue
+    if (ctl.world == 1) {
+      B200_DISPATCH_DT(dtype, {
+        fused_bucket_kernel<DT, 1, true><<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale, *sgd);
+      });
+    } else if (uint64_t(nvec) * 16 <= kLLMaxBytes) {
+      const uint32_t nwords = nvec * 4;
+      const int ll_grid = static_cast<int>((nwords + kLLWordsPerCta - 1) / kLLWordsPerCta);
+      B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
+                         fused_ll_kernel<DT, WS, true>
+                             <<<ll_grid, kLLThreads, 0, s>>>(tt, pt, ctl, bucket_off, nwords, scale, *sgd);
+                       }));
+    } else {
+      B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
+                         fused_bucket_kernel<DT, WS, true>
+                             <<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale, *sgd);
+                       }));
+    }
+    return cudaGetLastError();
+  }
   if (ctl.world == 1) {
     B200_DISPATCH_DT(dtype, {
-      fused_bucket_kernel<DT, 1><<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale);
+      fused_bucket_kernel<DT, 1><<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale, none);
     });
   } else if (uint64_t(nvec) * 16 <= kLLMaxBytes) {
     const uint32_t nwords = nvec * 4;
     const int ll_grid = static_cast<int>((nwords + kLLWordsPerCta - 1) / kLLWordsPerCta);
     B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
-                       fused_ll_kernel<DT, WS><<<ll_grid, kLLThreads, 0, s>>>(tt, pt, ctl, bucket_off, nwords, scale);
+                       fused_ll_kernel<DT, WS>
+                           <<<ll_grid, kLLThreads, 0, s>>>(tt, pt, ctl, bucket_off, nwords, scale, none);
                      }));
   } else {
     B200_DISPATCH_DT(dtype, B200_DISPATCH_WS(ctl.world, {
                        fused_bucket_kernel<DT, WS>
-                           <<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale);
+                           <<<grid, kFusedThreads, 0, s>>>(tt, pt, ctl, bucket_off, nvec, scale, none);
                      }));
   }
   return cudaGetLastError();
@@ -1179,6 +1325,8 @@ cudaError_t prepare_ws() {
   if ((e = preload(oneshot_kernel<DT, WS>)) != cudaSuccess) return e;
   if ((e = preload(twoshot_kernel<DT, WS>)) != cudaSuccess) return e;
   if ((e = preload(fused_bucket_kernel<DT, WS>)) != cudaSuccess) return e;
+  if ((e = preload(fused_bucket_kernel<DT, WS, true>)) != cudaSuccess) return e;
+  if ((e = preload(fused_ll_kernel<DT, WS, true>)) != cudaSuccess) return e;
   return preload(fused_ll_kernel<DT, WS>);
 }
 
@@ -1192,6 +1340,8 @@ cudaError_t prepare_dt(int world) {
   if ((e = preload(multi_tensor_copy_kernel<DT, false, 8>)) != cudaSuccess) return e;
   if ((e = preload(multi_tensor_copy_kernel<DT, true, 8>)) != cudaSuccess) return e;
   if ((e = preload(fused_bucket_kernel<DT, 1>)) != cudaSuccess) return e;
+  if ((e = preload(fused_bucket_kernel<DT, 1, true>)) != cudaSuccess) return e;
+  if ((e = preload(multi_tensor_copy_kernel<DT, true, 4, true>)) != cudaSuccess) return e;
   if ((e = preload(nvls_kernel<DT, 2>)) != cudaSuccess) return e;
   if ((e = preload(nvls_kernel<DT, 4>)) != cudaSuccess) return e;
   if ((e = preload(nvls_kernel<DT, 8>)) != cudaSuccess) return e;

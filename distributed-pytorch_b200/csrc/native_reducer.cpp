@@ -32,6 +32,10 @@ using fn_flatten = int (*)(void*, const void* const*, const uint64_t*, const uin
 using fn_unflatten = int (*)(void*, void* const*, const uint64_t*, const uint64_t*, int, int, uint64_t, void*);
 using fn_allreduce = int (*)(void*, uint64_t, uint64_t, uint64_t, int, int, int, float, void*);
 using fn_fused = int (*)(void*, void* const*, const uint64_t*, const uint64_t*, int, int, uint64_t, uint64_t, float, void*);
+using fn_unflatten_sgd = int (*)(void*, void* const*, void* const*, const uint64_t*, const uint64_t*, int, int, uint64_t,
+                                 float, void*);
+using fn_fused_sgd = int (*)(void*, void* const*, void* const*, const uint64_t*, const uint64_t*, int, int, uint64_t,
+                             uint64_t, float, float, void*);
 using fn_poll = int (*)(void*);
 using fn_last_error = const char* (*)(void*);
 
@@ -69,6 +73,14 @@ class NativeReducer {
     unflatten_ = reinterpret_cast<fn_unflatten>(need("b200ddp_unflatten"));
     allreduce_ = reinterpret_cast<fn_allreduce>(need("b200ddp_allreduce"));
     fused_ = reinterpret_cast<fn_fused>(need("b200ddp_fused_bucket"));
+    {  // optional: the optimizer-epilogue entry points (absent from the recording tables of the CPU tests)
+      auto u = fns.find("b200ddp_unflatten_sgd");
+      auto f = fns.find("b200ddp_fused_bucket_sgd");
+      if (u != fns.end() && f != fns.end()) {
+        unflatten_sgd_ = reinterpret_cast<fn_unflatten_sgd>(u->second);
+        fused_sgd_ = reinterpret_cast<fn_fused_sgd>(f->second);
+      }
+    }
     poll_ = reinterpret_cast<fn_poll>(need("b200ddp_poll_error"));
     last_error_ = reinterpret_cast<fn_last_error>(need("b200ddp_last_error"));
     scale_ = 1.0f / static_cast<float>(world_);
@@ -151,6 +163,14 @@ class NativeReducer {
   void disarm() {
     std::lock_guard<std::mutex> lk(mu_);
     armed_ = false;
+  }
+
+  // optimizer epilogue for the coming backward: lr > 0 makes the kernels that write the averaged gradient back also
+  // apply p <- p - lr g (DistributedDataParallel.fuse_optimizer decides per iteration); 0 = off
+  void set_sgd(double lr) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (lr != 0.0 && (!unflatten_sgd_ || !fused_sgd_)) throw std::runtime_error("the optimizer-epilogue entry points are missing");
+    sgd_lr_ = static_cast<float>(lr);
   }
 
   // an armed iteration that will never finish (aborted graph capture): forget it
@@ -239,9 +259,16 @@ class NativeReducer {
     void* cur = current_stream(params_[bk.params[0]]);
     int rc = stream_wait_(ctx_, comm_stream_, cur);
     if (rc) fail("stream_wait", rc);
+    const bool sgd = sgd_lr_ != 0.0f && bk.views.empty();
+    if (sgd) {
+      pptrs_.resize(n);
+      for (size_t k = 0; k < n; ++k) pptrs_[k] = params_[bk.params[k]].data_ptr();
+    }
     if (bk.fused) {
-      rc = fused_(ctx_, ptrs_.data(), bk.offs.data(), bk.lens.data(), static_cast<int>(n), bk.dtype, bk.arena_off,
-                  bk.nbytes, scale_, comm_stream_);
+      rc = sgd ? fused_sgd_(ctx_, ptrs_.data(), pptrs_.data(), bk.offs.data(), bk.lens.data(), static_cast<int>(n),
+                            bk.dtype, bk.arena_off, bk.nbytes, scale_, sgd_lr_, comm_stream_)
+               : fused_(ctx_, ptrs_.data(), bk.offs.data(), bk.lens.data(), static_cast<int>(n), bk.dtype, bk.arena_off,
+                        bk.nbytes, scale_, comm_stream_);
       if (rc) fail("fused_bucket", rc);
       ++launches_;
     } else {
@@ -253,8 +280,10 @@ class NativeReducer {
         if (rc) fail("allreduce", rc);
       }
       if (bk.views.empty()) {
-        rc = unflatten_(ctx_, ptrs_.data(), bk.offs.data(), bk.lens.data(), static_cast<int>(n), bk.dtype, bk.out_off,
-                        comm_stream_);
+        rc = sgd ? unflatten_sgd_(ctx_, ptrs_.data(), pptrs_.data(), bk.offs.data(), bk.lens.data(), static_cast<int>(n),
+                                  bk.dtype, bk.out_off, sgd_lr_, comm_stream_)
+                 : unflatten_(ctx_, ptrs_.data(), bk.offs.data(), bk.lens.data(), static_cast<int>(n), bk.dtype,
+                              bk.out_off, comm_stream_);
         if (rc) fail("unflatten", rc);
         launches_ += world_ > 1 ? 3 : 2;
       } else {
@@ -321,7 +350,10 @@ class NativeReducer {
   std::vector<Bucket> buckets_;
   std::vector<int64_t> param_bucket_;
   std::vector<char> seen_;
-  std::vector<void*> ptrs_;
+  std::vector<void*> ptrs_, pptrs_;
+  float sgd_lr_ = 0.0f;
+  fn_unflatten_sgd unflatten_sgd_ = nullptr;
+  fn_fused_sgd fused_sgd_ = nullptr;
   std::vector<at::Tensor> keepalive_;
   std::vector<int64_t> ready_order_, launched_;
   size_t next_bucket_ = 0;
@@ -350,6 +382,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("prepare", &NativeReducer::prepare, py::call_guard<py::gil_scoped_release>())
       .def("disarm", &NativeReducer::disarm)
       .def("abort", &NativeReducer::abort)
+      .def("set_sgd", &NativeReducer::set_sgd)
       .def("take_ready_order", &NativeReducer::take_ready_order)
       .def("iterations", &NativeReducer::iterations)
       .def("launches", &NativeReducer::launches)

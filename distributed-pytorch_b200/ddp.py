@@ -145,6 +145,47 @@ class DistributedDataParallel(nn.Module):
                                f"between ranks (signatures {sigs})")
 
     # ---- forward -------------------------------------------------------------------------------------
+    def fuse_optimizer(self, optimizer: torch.optim.Optimizer) -> bool:
+        """Opt-in (second half): let the kernels that write the averaged gradient back also apply
+        the optimizer step, ``p <- p - lr * g``, so the reference's ``self.optimizer.step()`` (ref:multigpu.py:43;
+        plain ``SGD(lr=1e-3)``, :68) has nothing left to do — one pass over the parameters and one launch less
+        per step.  Only plain SGD is fused (no momentum, weight decay, dampening, nesterov or maximize; every
+        parameter of the optimizer contiguous and reduced by this DDP; not with ``gradient_as_bucket_view``);
+        anything else returns False and changes nothing.
+
+        This moves the update INTO ``backward()``: code that runs between ``backward()`` and ``step()`` (gradient
+        clipping, loss scaling, skipping a step) sees gradients whose update has already been applied — which is why
+        it is opt-in (``B200DDP_FUSE_SGD=1`` makes the script Trainers call it).  A backward that starts with
+        gradients already present (accumulation) or runs under ``no_sync()`` is never fused: the optimizer then
+        steps itself.  ``optimizer.step`` is wrapped, the optimizer object stays the caller's."""
+        if getattr(self, "_fused_optimizer", None) is not None:
+            return self._fused_optimizer is optimizer
+        if type(optimizer) is not torch.optim.SGD or self.gradient_as_bucket_view:
+            return False
+        if not hasattr(self.engine, "sgd_lr"):
+            return False
+        groups = optimizer.param_groups
+        mine = {id(p) for p in self.reducer.params}
+        owned = [p for g in groups for p in g["params"]]
+        if len(groups) != 1 or {id(p) for p in owned} != mine or not all(p.is_contiguous() for p in owned):
+            return False
+        g = groups[0]
+        if g.get("momentum", 0) or g.get("weight_decay", 0) or g.get("dampening", 0) or g.get("nesterov", False) \
+                or g.get("maximize", False) or g.get("differentiable", False):
+            return False
+        reducer = self.reducer
+        reducer.sgd_lr_source = lambda: optimizer.param_groups[0]["lr"]
+        plain_step = optimizer.step
+
+        def step(closure=None):
+            if closure is None and reducer.consume_fused_update():
+                return None  # the bucket kernels of the backward that just finished applied p <- p - lr g
+            return plain_step(closure) if closure is not None else plain_step()
+
+        optimizer.step = step
+        self._fused_optimizer = optimizer
+        return True
+
     def check_health(self, sync: bool = True) -> None:
         """Raise if a kernel of this rank timed out on a peer (the step's gradients are then NOT the average).
         The script Trainers call this before writing a checkpoint."""

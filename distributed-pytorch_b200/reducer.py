@@ -106,6 +106,11 @@ class P2PEngine(BucketEngine):
         #: become views of the reduced bucket in the arena instead of being copied back (no unflatten pass)
         self.grad_views = False
         self._view_cache: Dict[int, List[torch.Tensor]] = {}
+        #: optimizer epilogue (opt-in, DistributedDataParallel.fuse_optimizer): the learning rate the kernels that
+        #: write the averaged gradient back also apply to the parameter (p <- p - lr g), or None; and the reduced
+        #: parameters in Reducer order (set by the Reducer)
+        self.sgd_lr: Optional[float] = None
+        self.params: Sequence[torch.Tensor] = ()
 
     # ---- planning -----------------------------------------------------------------------------------
     def plan(self, buckets: List[BucketSpec]) -> None:
@@ -163,9 +168,11 @@ class P2PEngine(BucketEngine):
     def _table(self, bucket: BucketSpec, tensors: Sequence[torch.Tensor]) -> TensorTable:
         ptrs = [t.data_ptr() for t in tensors]
         cached = self._tables.get(bucket.index)
-        if cached is not None and cached.key == tuple(ptrs):
+        want_params = self.sgd_lr is not None
+        if cached is not None and cached.key == tuple(ptrs) and (cached.params is not None) == want_params:
             return cached
-        table = TensorTable(ptrs, bucket.offsets_el, bucket.lengths_el)
+        params = [self.params[i].data_ptr() for i in bucket.param_indices] if want_params else None
+        table = TensorTable(ptrs, bucket.offsets_el, bucket.lengths_el, params)
         self._tables[bucket.index] = table
         return table
 
@@ -197,14 +204,21 @@ class P2PEngine(BucketEngine):
                                self.max_ctas, s)
             self._keepalive.extend(work)  # the flatten kernel on the side stream still reads them
             return self._bucket_views(bucket, grads)
+        lr = self.sgd_lr  # optimizer epilogue (parameters are contiguous: checked by fuse_optimizer)
         if bucket.fused:
-            comm.fused_bucket(table, bucket.dtype_code, bucket.arena_off, bucket.nbytes, self.scale, s)
+            if lr is not None:
+                comm.fused_bucket_sgd(table, bucket.dtype_code, bucket.arena_off, bucket.nbytes, self.scale, lr, s)
+            else:
+                comm.fused_bucket(table, bucket.dtype_code, bucket.arena_off, bucket.nbytes, self.scale, s)
         else:
             comm.flatten_scale(table, bucket.dtype_code, bucket.arena_off, self.scale, s)
             if self.world_size > 1:
                 comm.allreduce(bucket.arena_off, bucket.out_off, bucket.nbytes, bucket.dtype_code, bucket.algo,
                                self.max_ctas, s)
-            comm.unflatten(table, bucket.dtype_code, bucket.out_off, s)
+            if lr is not None:
+                comm.unflatten_sgd(table, bucket.dtype_code, bucket.out_off, lr, s)
+            else:
+                comm.unflatten(table, bucket.dtype_code, bucket.out_off, s)
         if work is not grads:
             with torch.cuda.stream(self.stream):
                 for g, w in zip(grads, work):
@@ -362,6 +376,13 @@ class Reducer:
             self._sizes, self._keys, [self.first_bucket_bytes_cap, self.bucket_bytes_cap])
         self.buckets: List[BucketSpec] = []
         self._install(list(reversed(indices)))
+        if hasattr(engine, "sgd_lr"):
+            engine.params = self.params
+        #: optimizer epilogue (DistributedDataParallel.fuse_optimizer): a callable returning the current learning
+        #: rate, or None
+        self.sgd_lr_source = None
+        self._sgd_armed = False
+        self._sgd_mark = -1  # the iteration count when the epilogue was last armed
         self.has_rebuilt = False
         self._rebuild_pending = False
         self.armed = False
@@ -456,9 +477,33 @@ class Reducer:
         return [b.payload_bytes for b in self.buckets]
 
     # ---- per-iteration protocol ----------------------------------------------------------------------
+    def _arm_sgd(self) -> None:
+        """Decide, per iteration, whether the bucket kernels also apply the optimizer step: only when every
+        gradient starts from None (then the bucket holds THE gradient of this step; with gradients carried over
+        from earlier backwards — accumulation — the optimizer must see the accumulated value and steps itself)."""
+        lr = None
+        if self.sgd_lr_source is not None and self.require_sync and all(p.grad is None for p in self.params):
+            lr = float(self.sgd_lr_source())
+        self._sgd_armed = lr is not None
+        self.engine.sgd_lr = lr
+        if self._native is not None:
+            self._native.set_sgd(lr if lr is not None else 0.0)
+
+    def consume_fused_update(self) -> bool:
+        """True exactly once after a backward whose kernels applied the optimizer step (the patched
+        ``optimizer.step`` then has nothing left to do)."""
+        it = int(self._native.iterations()) if self._native is not None else self.iterations
+        if self._sgd_armed and it > self._sgd_mark:  # the armed backward has finished (finalize counted it)
+            self._sgd_armed = False
+            return True
+        return False
+
     def prepare_for_backward(self) -> None:
         """Arm the reducer for the backward of the forward that just ran
         (Reducer::prepare_for_backward, called from DDP._post_forward, distributed.py:1648)."""
+        if self.sgd_lr_source is not None or self._sgd_armed:
+            self._sgd_mark = int(self._native.iterations()) if self._native is not None else self.iterations
+            self._arm_sgd()
         if self._native is not None:
             if not self.has_rebuilt and self._native.iterations() >= 1:
                 # the one-time rebuild, driven from here like torch drives it from the next forward

@@ -147,6 +147,17 @@ int b200ddp_fused_bucket(b200ddp_ctx* ctx, void* const* grad_ptrs, const uint64_
                          uint64_t bucket_bytes, float scale, void* stream);
 int b200ddp_max_table_tensors(void);
 uint64_t b200ddp_fused_max_bytes(void);
+
+/* Optional optimizer epilogue (opt-in from the host: DistributedDataParallel.fuse_optimizer).  The same
+ * two calls with one more pointer table: wherever the kernel writes the averaged gradient g_i back it also applies plain
+ * SGD to the parameter the gradient belongs to, param_i <- fma(-lr, g_i, param_i) — what torch.optim.SGD(lr) without
+ * momentum / weight decay computes in its own pass over all parameters (ref:multigpu.py:43,68).  param_ptrs[i] may be
+ * NULL (that tensor is only un-flattened); parameters are laid out like their gradients (same dtype, same length). */
+int b200ddp_unflatten_sgd(b200ddp_ctx* ctx, void* const* grad_ptrs, void* const* param_ptrs, const uint64_t* off_el,
+                          const uint64_t* len_el, int n, int dtype, uint64_t bucket_off, float lr, void* stream);
+int b200ddp_fused_bucket_sgd(b200ddp_ctx* ctx, void* const* grad_ptrs, void* const* param_ptrs,
+                             const uint64_t* off_el, const uint64_t* len_el, int n, int dtype, uint64_t bucket_off,
+                             uint64_t bucket_bytes, float scale, float lr, void* stream);
 uint64_t b200ddp_fused_region_bytes(b200ddp_ctx* ctx, uint64_t bucket_bytes);
 /* the same for a world size given explicitly (no context: callers size the arena BEFORE b200ddp_init) */
 uint64_t b200ddp_fused_region_bytes_for(int world, uint64_t bucket_bytes);

@@ -741,3 +741,135 @@ def test_replayed_step_follows_a_learning_rate_change(pg1, monkeypatch):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
     finally:
         multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
+
+
+# ---------------------------------------------------------------------------------------------------
+# optimizer epilogue (opt-in): the bucket kernels also apply plain SGD
+# ---------------------------------------------------------------------------------------------------
+def _train_pair(pg, build, loss_fn, batches, lr, fuse, cap_mb=None, graph=False):
+    from b200ddp import DDP
+
+    torch.manual_seed(7)
+    model = build().cuda()
+    plain = copy.deepcopy(model)
+    opt = torch.optim.SGD(model.parameters(), lr=lr)
+    popt = torch.optim.SGD(plain.parameters(), lr=lr)
+    ddp = DDP(model, device_ids=[0], **({} if cap_mb is None else {"bucket_cap_mb": cap_mb}))
+    assert ddp.fuse_optimizer(opt) == fuse or not fuse
+    n0 = ddp.engine.comm.launch_count
+    for x, y in batches:
+        opt.zero_grad()
+        loss_fn(ddp(x), y).backward()
+        opt.step()
+        popt.zero_grad()
+        loss_fn(plain(x), y).backward()
+        popt.step()
+    torch.cuda.synchronize()
+    return model, plain, ddp, ddp.engine.comm.launch_count - n0
+
+
+def test_fused_sgd_world1_matches_torch_sgd(pg1):
+    """fuse_optimizer at world 1: the toy model (fused single-launch kernel) and a multi-bucket MLP (unflatten kernel,
+    ragged tensors), fp32 and bf16: the trajectory of torch.optim.SGD within one rounding per step."""
+    gen = torch.Generator().manual_seed(0)
+    toy_batches = [(torch.rand(32, 20, generator=gen).cuda(), torch.rand(32, 1, generator=gen).cuda()) for _ in range(6)]
+    model, plain, ddp, launches = _train_pair(pg1, lambda: torch.nn.Linear(20, 1), torch.nn.functional.mse_loss,
+                                              toy_batches, 1e-2, True)
+    assert launches == 6  # one fused launch per step, the optimizer launched nothing of ours
+    for p, q in zip(model.parameters(), plain.parameters()):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+    ddp.shutdown()
+
+    def mlp():
+        return torch.nn.Sequential(torch.nn.Linear(20, 513), torch.nn.ReLU(), torch.nn.Linear(513, 511), torch.nn.ReLU(),
+                                   torch.nn.Linear(511, 7))
+
+    batches = [(torch.rand(16, 20, generator=gen).cuda(), torch.rand(16, 7, generator=gen).cuda()) for _ in range(5)]
+    model, plain, ddp, _ = _train_pair(pg1, mlp, torch.nn.functional.mse_loss, batches, 5e-2, True, cap_mb=0.5)
+    assert any(not b.fused for b in ddp.reducer.buckets) and ddp.reducer.has_rebuilt
+    for p, q in zip(model.parameters(), plain.parameters()):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+    ddp.shutdown()
+
+    bbatches = [(x.bfloat16(), y.bfloat16()) for x, y in batches]
+    model, plain, ddp, _ = _train_pair(pg1, lambda: mlp().bfloat16(), torch.nn.functional.mse_loss, bbatches, 5e-2, True,
+                                       cap_mb=0.5)
+    for p, q in zip(model.parameters(), plain.parameters()):
+        assert torch.allclose(p.float(), q.float(), rtol=2 ** -7, atol=2 ** -9)
+    ddp.shutdown()
+
+
+def test_fused_sgd_under_the_script_trainer_and_graph_replay(pg1, monkeypatch):
+    """B200DDP_FUSE_SGD=1: the script Trainer fuses its plain SGD; eager steps, the captured step and a learning-rate
+    change in between all follow plain training."""
+    from b200ddp import multigpu, utils
+
+    monkeypatch.setenv("B200DDP_FUSE_SGD", "1")
+    monkeypatch.delenv("B200DDP_GRAPH", raising=False)
+    torch.manual_seed(0)
+    ds = utils.MyTrainDataset(32 * 14, seed=4)
+    model = torch.nn.Linear(20, 1)
+    plain = copy.deepcopy(model).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    multigpu.Trainer.loss_fn = staticmethod(torch.nn.MSELoss())
+    try:
+        trainer = multigpu.Trainer(model, [], opt, 0, save_every=10**9)
+        assert trainer.model._fused_optimizer is opt
+        xs, ys = ds.x.cuda(), ds.y.cuda()
+        batches = [(xs[i:i + 32], ys[i:i + 32]) for i in range(0, len(ds), 32)]
+        for i, (x, y) in enumerate(batches):
+            if i == 8:
+                opt.param_groups[0]["lr"] = 0.1
+            trainer._run_batch(x, y)
+        assert trainer._state()["slots"].get("dev") is not None and trainer.graph_kernel_launches == 1
+        torch.cuda.synchronize()
+        _plain_steps(plain, torch.optim.SGD(plain.parameters(), lr=1e-2), batches[:8])
+        _plain_steps(plain, torch.optim.SGD(plain.parameters(), lr=0.1), batches[8:])
+        for p, q in zip(trainer.model.module.parameters(), plain.parameters()):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    finally:
+        multigpu.Trainer.loss_fn = staticmethod(torch.nn.CrossEntropyLoss())
+
+
+def test_fused_sgd_loopback_ws2_ll_and_unflatten_paths():
+    """Two ranks on one GPU with the optimizer epilogue: the LL kernel (toy) and the three-kernel path (MLP) leave
+    both ranks with identical weights that follow SGD on the averaged gradient."""
+    from b200ddp.comm import P2PComm
+
+    for build, dims, cap in ((lambda: torch.nn.Linear(20, 1), (20, 1), None),
+                             (lambda: torch.nn.Sequential(torch.nn.Linear(20, 300), torch.nn.ReLU(), torch.nn.Linear(300, 300),
+                                                          torch.nn.ReLU(), torch.nn.Linear(300, 3)), (20, 3), 0.25)):
+        comms = P2PComm.loopback_world(2, 0, 16 << 20)
+        for c in comms:
+            c.set_timeout_ms(10000)
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        torch.manual_seed(5)
+        base = build().cuda()
+        models = [copy.deepcopy(base) for _ in range(2)]
+        ref = copy.deepcopy(base)
+        kw = {} if cap is None else {"bucket_cap_mb": cap}
+        ddps = _loopback_ddp_world(models, comms, streams, 1 << 20, **kw)
+        opts = [torch.optim.SGD(m.parameters(), lr=5e-2) for m in models]
+        ropt = torch.optim.SGD(ref.parameters(), lr=5e-2)
+        for d, o in zip(ddps, opts):
+            assert d.fuse_optimizer(o)
+        gen = torch.Generator().manual_seed(1)
+        for step in range(4):
+            xs = [torch.rand(16, dims[0], generator=gen).cuda() for _ in range(2)]
+            ys = [torch.rand(16, dims[1], generator=gen).cuda() for _ in range(2)]
+            torch.cuda.synchronize()
+            _loopback_step(ddps, models, streams, xs, ys, torch.nn.functional.mse_loss)
+            for r in range(2):
+                with torch.cuda.stream(streams[r]):
+                    opts[r].step()
+            ropt.zero_grad()
+            (0.5 * (torch.nn.functional.mse_loss(ref(xs[0]), ys[0]) + torch.nn.functional.mse_loss(ref(xs[1]), ys[1]))).backward()
+            ropt.step()
+            torch.cuda.synchronize()
+            for c in comms:
+                c.poll_error()
+        for p0, p1, q in zip(models[0].parameters(), models[1].parameters(), ref.parameters()):
+            assert torch.equal(p0, p1)
+            assert torch.allclose(p0, q, rtol=1e-5, atol=1e-6)
+        for d in ddps:
+            d.shutdown()

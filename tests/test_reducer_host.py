@@ -415,3 +415,64 @@ def test_deferred_rebuild_moves_live_bucket_views_to_private_storage():
     assert eng.cloned_before_plan == [True] * 6
     for p, k in zip(model.parameters(), kept):
         assert torch.allclose(p.grad, 2 * k)  # accumulated on top of the preserved values
+
+
+def test_fuse_optimizer_eligibility_and_per_iteration_arming():
+    """DistributedDataParallel.fuse_optimizer (opt-in optimizer epilogue): only plain SGD on exactly this DDP's
+    contiguous parameters; armed per iteration only when every gradient starts from None; the wrapped
+    optimizer.step is skipped exactly once after an armed backward and steps normally otherwise."""
+    class SgdEngine(RecordingEngine):
+        def __init__(self):
+            super().__init__()
+            self.sgd_lr, self.params, self.seen = None, (), []
+
+        def reduce_bucket(self, bucket, grads):
+            super().reduce_bucket(bucket, grads)
+            self.seen.append(self.sgd_lr)
+
+    # not eligible: momentum, Adam, foreign parameters, an engine without the epilogue
+    m = _mlp()
+    assert not DDP(m, _engine=SgdEngine()).fuse_optimizer(torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9))
+    m = _mlp()
+    assert not DDP(m, _engine=SgdEngine()).fuse_optimizer(torch.optim.Adam(m.parameters(), lr=0.1))
+    m = _mlp()
+    assert not DDP(m, _engine=SgdEngine()).fuse_optimizer(torch.optim.SGD(list(m.parameters())[:2], lr=0.1))
+    m = _mlp()
+    assert not DDP(m, _engine=RecordingEngine()).fuse_optimizer(torch.optim.SGD(m.parameters(), lr=0.1))
+
+    eng = SgdEngine()
+    model = _mlp()
+    opt = torch.optim.SGD(model.parameters(), lr=0.25)
+    ddp = DDP(model, _engine=eng)
+    assert ddp.fuse_optimizer(opt) and ddp.fuse_optimizer(opt)
+    x = torch.randn(8, 20)
+    before = [p.detach().clone() for p in model.parameters()]
+    opt.zero_grad()
+    ddp(x).square().mean().backward()
+    assert eng.seen and all(lr == 0.25 for lr in eng.seen)  # every bucket was launched with the epilogue
+    opt.step()  # the (fake) kernels "applied" the update: the optimizer must not apply it again
+    assert all(torch.equal(p, b) for p, b in zip(model.parameters(), before))
+    opt.step()  # a second call without a new backward is a normal step
+    assert not all(torch.equal(p, b) for p, b in zip(model.parameters(), before))
+    # gradient accumulation (no zero_grad): not armed, the optimizer steps itself on the accumulated gradient
+    eng.seen.clear()
+    opt.param_groups[0]["lr"] = 0.5
+    before = [p.detach().clone() for p in model.parameters()]
+    ddp(x).square().mean().backward()
+    assert eng.seen and all(lr is None for lr in eng.seen)
+    opt.step()
+    assert not all(torch.equal(p, b) for p, b in zip(model.parameters(), before))
+    # armed again after zero_grad, with the new learning rate; no_sync never arms
+    eng.seen.clear()
+    opt.zero_grad()
+    ddp(x).square().mean().backward()
+    assert all(lr == 0.5 for lr in eng.seen)
+    opt.step()
+    eng.seen.clear()
+    opt.zero_grad()
+    with ddp.no_sync():
+        ddp(x).square().mean().backward()
+    assert eng.seen == []
+    before = [p.detach().clone() for p in model.parameters()]
+    opt.step()
+    assert not all(torch.equal(p, b) for p, b in zip(model.parameters(), before))
