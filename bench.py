@@ -90,6 +90,8 @@ def parse_args():
     ap.add_argument("--blocks", type=int, default=None, help="timed blocks of `steps` steps (default: by workload)")
     ap.add_argument("--bucket-cap-mb", type=float, default=None, help="DDP bucket_cap_mb (the slices sweep)")
     ap.add_argument("--views", action="store_true", help="gradient_as_bucket_view=True (both our DDP and the comparator)")
+    ap.add_argument("--fuse-sgd", action="store_true",
+                    help="opt-in optimizer epilogue (B200DDP_FUSE_SGD=1): the bucket kernels also apply the SGD step")
     ap.add_argument("--no-sweep", action="store_true", help="skip the bucket-size sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the ResNet-50 leg of toy runs")
@@ -864,7 +866,10 @@ def main_b200(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
     host, devb, shard = make_batches(torch, wl, args.workload, bsz, local, rank)
+    if args.fuse_sgd and not stock:
+        os.environ["B200DDP_FUSE_SGD"] = "1"
     trainer = build_trainer(torch, wl, args.workload, bsz, local, rank, stock, args.bucket_cap_mb, args.views, args.graph)
+    os.environ.pop("B200DDP_FUSE_SGD", None)  # the comparator and ResNet-50 legs stay on the default path
     ddp = trainer.model
 
     class _NoComm:  # stock DDP has no b200ddp communicator
@@ -983,6 +988,7 @@ def main_b200(args):
                         "mem_mode": comm.mem_mode, "multicast": comm.has_multicast, "cuda_graph": replayed,
                         "graph_mode": mode_wanted, "arena_bytes": comm.arena_bytes,
                         "gradient_as_bucket_view": bool(ddp.gradient_as_bucket_view),
+                        "fused_sgd": getattr(ddp, "_fused_optimizer", None) is not None,
                         "hook_loop": "C++" if getattr(ddp.reducer, "_native", None) is not None else "Python"},
         "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline_step": roofline_step,
         "bucket_sweep": sweep, "cpu_baseline": cpu, "eager": eager, "nccl_ddp": nccl_ddp, "parity": parity,
