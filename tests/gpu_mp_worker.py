@@ -153,7 +153,46 @@ def hook_vs_nccl(rank, world, workload="slices", steps=3):
     return res
 
 
-FUNCS = dict(raw_allreduce=raw_allreduce, ddp_vs_nccl=ddp_vs_nccl, hook_vs_nccl=hook_vs_nccl)
+def fused_sgd_vs_nccl(rank, world, workload="mlp", steps=5, bucket_cap_mb=None):
+    """Our DDP with the optimizer epilogue (fuse_optimizer) against stock torch-DDP/NCCL + torch.optim.SGD: the
+    weights after `steps` steps (small fused buckets and, for `slices`, 25 MiB buckets through the unflatten kernel)."""
+    import copy
+
+    from b200ddp import DDP, workloads
+
+    wl = workloads.get(workload)
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(4321)
+    base = wl.build().to(dev)
+    ours_m, ref_m = copy.deepcopy(base), copy.deepcopy(base)
+    kw = {} if bucket_cap_mb is None else {"bucket_cap_mb": bucket_cap_mb}
+    ours = DDP(ours_m, device_ids=[rank], **kw)
+    ref = torch.nn.parallel.DistributedDataParallel(ref_m, device_ids=[rank], **kw)
+    o1 = torch.optim.SGD(ours_m.parameters(), lr=1e-2)
+    o2 = torch.optim.SGD(ref_m.parameters(), lr=1e-2)
+    fused = ours.fuse_optimizer(o1)
+    gen = torch.Generator().manual_seed(99 + rank)
+    for step in range(steps):
+        x, y = wl.batch(16, dev, gen)
+        for m, o in ((ours, o1), (ref, o2)):
+            o.zero_grad()
+            wl.loss(m(x), y).backward()
+            o.step()
+    torch.cuda.synchronize()
+    worst = 0.0
+    for p, q in zip(ours_m.parameters(), ref_m.parameters()):
+        denom = float(q.double().abs().max())
+        num = float((p.double() - q.double()).abs().max())
+        worst = max(worst, num / denom if denom > 0 else num)
+    flat = torch.cat([p.detach().reshape(-1) for p in ours_m.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    return dict(fused=bool(fused), worst_rel_weights=worst, weights_equal_across_ranks=all(torch.equal(g, gathered[0]) for g in gathered),
+                fused_buckets=[b.fused for b in ours.reducer.buckets])
+
+
+FUNCS = dict(raw_allreduce=raw_allreduce, ddp_vs_nccl=ddp_vs_nccl, hook_vs_nccl=hook_vs_nccl,
+             fused_sgd_vs_nccl=fused_sgd_vs_nccl)
 
 
 def entry(rank, world, port, fn_name, kw, ret):

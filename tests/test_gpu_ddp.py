@@ -381,6 +381,19 @@ def test_multigpu_baseline_configs_match_stock_nccl_ddp(workload, batch, tol):
 
 @needs_multi
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("workload", ["mlp", "slices"])
+def test_multigpu_fused_sgd_matches_stock_ddp_plus_torch_sgd(workload):
+    world = min(torch.cuda.device_count(), 8)
+    out = _spawn_mp("fused_sgd_vs_nccl", world, workload=workload)
+    print(f"fused SGD {workload} ws={world}: worst rel of the weights vs stock DDP/NCCL + torch SGD = "
+          f"{max(out[r]['worst_rel_weights'] for r in range(world)):.3e}")
+    for r in range(world):
+        assert out[r]["fused"] and out[r]["weights_equal_across_ranks"], out[r]
+        assert out[r]["worst_rel_weights"] <= 1e-6, out[r]
+
+
+@needs_multi
+@pytest.mark.timeout(900)
 def test_multigpu_comm_hook_shim_matches_stock_nccl_ddp():
     world = min(torch.cuda.device_count(), 8)
     out = _spawn_mp("hook_vs_nccl", world)
