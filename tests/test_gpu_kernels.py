@@ -448,3 +448,33 @@ def test_gather_rows_follows_the_cursor_and_wraps():
         assert int(cursor) == pos
     assert lib.b200ddp_gather_rows(shard.data_ptr(), whole.data_ptr(), None, 6, 0, bsz, full, cursor.data_ptr(), s) == -1
     assert "4-byte words" in _lib.last_error(None)
+
+
+@pytest.mark.parametrize("lens", [[20, 1], [30000, 5, 4099, 12001]], ids=["ll-84B", "one-barrier-184KB"])
+def test_fused_bucket_sgd_epilogue_on_loopback_worlds(world, lens):
+    """b200ddp_fused_bucket_sgd at ws in {2,3,4,8}: gradients = the oracle's average (bit-exact, as without the
+    epilogue) and parameters = fma(-lr, g_avg, p) on every rank (one rounding: compared in float64, <= 1 ulp)."""
+    ws = world.ws
+    lr = 0.125
+    offs = ao.padded_offsets(lens, "f32")
+    total = offs[-1] + (lens[-1] + 3) // 4 * 4
+    gens = [torch.Generator().manual_seed(40 + r) for r in range(ws)]
+    grads = [[_rand(n, "f32", g) for n in lens] for g in gens]
+    pgen = torch.Generator().manual_seed(3)
+    p0 = [_rand(n, "f32", pgen) for n in lens]
+    params = [[p.clone() for p in p0] for _ in range(ws)]
+    want_g = ao.ddp_average([[_storage(g, "f32") for g in gs] for gs in grads])
+    region = world.comms[0].fused_region_bytes(total * 4)
+    world.run(lambda r, c, s: c.clear(1 << 20, (region + 15) // 16 * 16, s))
+
+    def launch(r, c, s):
+        table = TensorTable([g.data_ptr() for g in grads[r]], offs, lens, [p.data_ptr() for p in params[r]])
+        c.fused_bucket_sgd(table, _lib.F32, 1 << 20, total * 4, 1.0 / ws, lr, s)
+
+    world.run(launch)
+    for r in range(ws):
+        for g, w, p, q in zip(grads[r], want_g, params[r], p0):
+            assert np.array_equal(_storage(g, "f32"), w)
+            want_p = (q.cpu().double() - lr * torch.from_numpy(w).double()).float()
+            err = (p.cpu().double() - want_p.double()).abs().max() / max(1e-30, float(want_p.abs().max()))
+            assert float(err) <= 2e-7, f"rank {r}: parameter update off by {float(err):.3e}"
