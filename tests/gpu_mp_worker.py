@@ -74,7 +74,7 @@ def raw_allreduce(rank, world, mem="vmm"):
     return res
 
 
-def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None, views=False, batch=16):
+def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None, views=False, batch=16, regrow_at=None):
     """Our DDP and stock torch-DDP/NCCL side by side: same seeded weights, same per-rank batches."""
     import copy
 
@@ -96,6 +96,12 @@ def ddp_vs_nccl(rank, world, workload="mlp", steps=4, bucket_cap_mb=None, views=
     worst = 0.0
     for step in range(steps):
         x, y = wl.batch(batch, dev, gen)
+        if regrow_at is not None and step == regrow_at:
+            # what a re-bucketing that outgrows the arena does (P2PEngine._grow_arena, collective): a new, larger
+            # communicator; the Reducer re-installs its buckets on it and re-binds the C++ hook loop
+            o1.zero_grad()
+            ours.engine._grow_arena(2 * ours.engine.comm.arena_bytes)
+            ours.reducer._install([list(b.param_indices) for b in ours.reducer.buckets])
         ref_m.load_state_dict(ours_m.state_dict())  # same weights going into every step
         o1.zero_grad()
         o2.zero_grad()

@@ -170,6 +170,41 @@ def test_gradient_as_bucket_view_world1(pg1):
     ddp.shutdown()
 
 
+@pytest.mark.parametrize("views", [False, True], ids=["copy-back", "grad-views"])
+def test_arena_regrow_world1(pg1, views):
+    """P2PEngine._grow_arena + Reducer._install on the new communicator (tables, bucket views and the C++ hook loop's
+    context are re-bound): training continues bit-for-bit like the plain model."""
+    from b200ddp import DDP, workloads
+
+    wl = workloads.get("mlp")
+    torch.manual_seed(2)
+    model = torch.nn.Sequential(torch.nn.Linear(20, 600), torch.nn.ReLU(), torch.nn.Linear(600, 600), torch.nn.ReLU(),
+                                torch.nn.Linear(600, 7)).cuda()
+    plain = copy.deepcopy(model)
+    ddp = DDP(model, device_ids=[0], bucket_cap_mb=1.0, gradient_as_bucket_view=views)
+    o1 = torch.optim.SGD(model.parameters(), lr=1e-2)
+    o2 = torch.optim.SGD(plain.parameters(), lr=1e-2)
+    gen = torch.Generator().manual_seed(8)
+    for step in range(5):
+        if step == 3:
+            o1.zero_grad()
+            old = ddp.engine.comm.arena_bytes
+            ddp.engine._grow_arena(2 * old)
+            ddp.reducer._install([list(b.param_indices) for b in ddp.reducer.buckets])
+            assert ddp.engine.comm.arena_bytes >= 2 * old
+        x, y = wl.batch(16, torch.device("cuda"), gen)
+        o1.zero_grad()
+        o2.zero_grad()
+        wl.loss(ddp(x), y).backward()
+        wl.loss(plain(x), y).backward()
+        torch.cuda.synchronize()
+        for p, q in zip(model.parameters(), plain.parameters()):
+            assert torch.equal(p.grad, q.grad), f"step {step}"
+        o1.step()
+        o2.step()
+    ddp.shutdown()
+
+
 def test_product_path_requires_cuda_module(pg1):
     from b200ddp import DDP
 
@@ -376,6 +411,19 @@ def test_multigpu_baseline_configs_match_stock_nccl_ddp(workload, batch, tol):
           f"algos {out[0]['algos']}")
     for r in range(world):
         assert out[r]["worst_rel"] <= tol, out[r]
+        assert out[r]["weights_equal_across_ranks"]
+
+
+@needs_multi
+@pytest.mark.timeout(900)
+def test_multigpu_arena_regrow_keeps_training_in_step():
+    """The arena is sized from the construction-time plan; a re-bucketing that needs more replaces the communicator
+    (collective).  Forced here after two steps on `slices` (25 MiB buckets + small ones): gradients keep matching
+    stock DDP/NCCL afterwards."""
+    world = min(torch.cuda.device_count(), 8)
+    out = _spawn_mp("ddp_vs_nccl", world, workload="slices", steps=4, regrow_at=2)
+    for r in range(world):
+        assert out[r]["worst_rel"] <= 1e-6, out[r]
         assert out[r]["weights_equal_across_ranks"]
 
 
