@@ -46,9 +46,11 @@ class GlooEngine(BucketEngine):
     fl32(1/ws), rank-ordered fp32 sum) on top of gloo all_gather, so that a CPU run of our Reducer can be
     compared with stock DDP.  Checker only."""
 
-    def __init__(self) -> None:
+    def __init__(self, sgd_epilogue: bool = False) -> None:
         self.rank, self.world_size = dist.get_rank(), dist.get_world_size()
         self.launched: List[int] = []
+        if sgd_epilogue:  # stands in for the product engine's optimizer epilogue (DDP.fuse_optimizer)
+            self.sgd_lr, self.params, self.epilogues = None, (), 0
 
     def plan(self, buckets):
         self.buckets = list(buckets)
@@ -66,6 +68,11 @@ class GlooEngine(BucketEngine):
         for g in grads:
             g.copy_(acc[off:off + g.numel()].view_as(g))
             off += g.numel()
+        if getattr(self, "sgd_lr", None) is not None:  # p <- p - lr g where the averaged gradient is written back
+            with torch.no_grad():
+                for i, g in zip(bucket.param_indices, grads):
+                    self.params[i].add_(g, alpha=-self.sgd_lr)
+            self.epilogues += 1
 
     def finalize(self):
         pass

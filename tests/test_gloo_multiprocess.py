@@ -46,6 +46,35 @@ def _replay_reference_trainer(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+def _replay_reference_trainer_fused(rank, world, port, ret):
+    """The same replay with the optimizer epilogue: `DDP.fuse_optimizer(opt)` arms the engine per iteration, the engine
+    applies p <- p - lr g where it writes the averaged gradient back, and the wrapped `opt.step()` does nothing."""
+    from b200ddp import DDP
+    from tests.helpers import GlooEngine
+
+    _init(rank, world, port)
+    try:
+        fx = torch.load(os.path.join(GOLD, "ref_trainer_ws2.pt"))["cases"]["mse"][rank]
+        model = torch.nn.Linear(20, 1)
+        model.load_state_dict({"weight": fx["w_before"][0][0], "bias": fx["w_before"][0][1]})
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+        eng = GlooEngine(sgd_epilogue=True)
+        ddp = DDP(model, _engine=eng)
+        fused = ddp.fuse_optimizer(opt)
+        ok = True
+        for step in range(4):
+            opt.zero_grad()
+            torch.nn.MSELoss()(ddp(fx["x"][step]), fx["y"][step]).backward()
+            after_backward = [p.detach().clone() for p in model.parameters()]
+            opt.step()  # must be a no-op: the engine already applied the update
+            ok = ok and all(torch.equal(p.detach(), a) for p, a in zip(model.parameters(), after_backward))
+            ok = ok and all(torch.allclose(p.detach(), ref, rtol=0, atol=1e-7) for p, ref in zip(model.parameters(), fx["w_after"][step]))
+            ok = ok and all(torch.equal(p.grad, ref) for p, ref in zip(model.parameters(), fx["ddp_grads"][step]))
+        ret[rank] = dict(fused=fused, ok=ok, epilogues=eng.epilogues)
+    finally:
+        dist.destroy_process_group()
+
+
 def _replay_stock_mlp(rank, world, port, ret):
     from b200ddp import DDP, workloads
     from tests.helpers import GlooEngine, rel_err
@@ -93,6 +122,14 @@ def test_ws2_replays_reference_trainer_bitwise():
         assert out[r]["exact"], f"rank {r}: gradients differ from the reference's DDP (worst rel {out[r]['worst']})"
         assert out[r]["worst"] <= 1e-6
         assert out[r]["buckets"] == [84] and out[r]["rebuilt"]
+
+
+@pytest.mark.timeout(300)
+def test_ws2_optimizer_epilogue_follows_the_reference_trainer():
+    out = _spawn(_replay_reference_trainer_fused, 2)
+    for r in range(2):
+        assert out[r]["fused"] and out[r]["epilogues"] == 4
+        assert out[r]["ok"], f"rank {r}: weights / gradients left the reference Trainer's golden trajectory"
 
 
 @pytest.mark.timeout(300)
