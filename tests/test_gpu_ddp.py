@@ -544,7 +544,7 @@ def test_host_batches_go_through_the_pipelined_graphs(pg1, monkeypatch, pipeline
             loss = torch.nn.functional.mse_loss(plain(x.cuda()), y.cuda())
             loss.backward()
             popt.step()
-            want.append(float(loss))
+            want.append(float(loss.detach()))
         # a PendingLoss of an OLD step has been overwritten by a later replay of the same slot: only the last two
         # are still meaningful, which is exactly the read-one-step-late protocol
         assert abs(got[-1].item() - want[-1]) <= 1e-5 * max(1.0, abs(want[-1]))
