@@ -28,6 +28,7 @@ runs = [("toy N=1 (final kernels)", "r31_bench_n1.json"),
         ("toy N=2 --graph off (every step eager, --steps 200)", "r32_bench_toy_eager_n2.json"),
         ("toy N=1, optimizer epilogue A/B: default", "r34_bench_n1_plain.json"),
         ("toy N=1, optimizer epilogue A/B: --fuse-sgd (same box, back to back)", "r34_bench_n1_fused.json"),
+        ("toy N=8 --fuse-sgd (no sweep / extra / nccl legs)", "r37_bench_n8_fused.json"),
         ("COMPARATOR --impl nccl toy N=2", "r22_nccl_n2.json")]
 with open(os.path.join(P, "r02_bench_lines.jsonl"), "w") as f:
     for label, name in runs:
