@@ -46,7 +46,8 @@ struct Ctl {
   int world;
 };
 
-// Multi-tensor table, passed BY VALUE as a kernel parameter (<= 4 KiB with the other arguments).
+// Multi-tensor table, passed BY VALUE as a kernel parameter (< 4 KiB with the other arguments; the opt-in SGD
+// instantiations add an SgdTable and use the > 4 KiB parameter space CUDA 12.1+ offers on sm_70 and later).
 // Tensor i occupies bucket vectors [off_vec[i], off_vec[i+1]) (16-byte units from the bucket start) and
 // holds len_el[i] elements starting at ptr[i].  off_vec is ascending; off_vec[n] closes the last tensor.
 struct TensorTable {

@@ -6,7 +6,10 @@
 //                             instead of one D2D launch per parameter.
 //   oneshot/twoshot/tma/nvls  ProcessGroupNCCL::allreduce -> ncclAllReduce(SUM) (ProcessGroupNCCL.hpp:856):
 //                             the kernel itself issues the NVLink traffic on peer-mapped arenas.
-//   fused_bucket_kernel       all three steps of a small bucket in a single launch.
+//   fused_bucket_kernel       all three steps of a small bucket in a single launch (one cross-GPU barrier);
+//   fused_ll_kernel           the same for buckets <= 32 KiB with NO barrier (data + tag in one 8-byte store).
+//   gather_rows_kernel        the per-batch `source.to(gpu_id)` of ref:multigpu.py:48-50 for a shard resident in HBM.
+//   (SGD instantiations)      fused_*/unflatten with an SgdTable also apply torch.optim.SGD's p -= lr g (opt-in).
 //
 // Design notes
 //   * Everything is a stream of 16-byte vectors (LDG.128/STG.128, L1::no_allocate): the path is pure
@@ -20,7 +23,8 @@
 //     launch carries no host-side generation counter and can be replayed from a CUDA graph.
 //     CTA b only ever depends on CTA b of the peers, so no grid-wide co-residency is needed.
 //   * Spins are bounded by %globaltimer; a timeout raises a flag in mapped host memory instead of
-//     hanging the GPU (a dead peer becomes a Python exception).
+//     hanging the GPU (a dead peer becomes a Python exception) and poisons the rank: the kernel returns
+//     without touching gradients, later collective kernels return at once, unflatten leaves .grad alone.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
