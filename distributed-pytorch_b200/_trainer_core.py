@@ -554,9 +554,12 @@ class TrainerCore:
         first = next(iter(self.train_data))[0]
         print(f"[GPU{self.gpu_id}] Epoch {epoch} | Batchsize: {len(first)} | Steps: {steps}")
         st = self._state()
-        if _truthy(os.environ.get("B200DDP_RESIDENT")) and st["mode"] != "off" and self.enable_resident_shard():
-            self._run_resident_epoch()
-            return
+        if _truthy(os.environ.get("B200DDP_RESIDENT")) and st["mode"] != "off":
+            if st["resident"] is not None and st.get("guard") != self._capture_guard():
+                self._drop_captures()  # e.g. a scheduler changed the learning rate between epochs: capture anew
+            if self.enable_resident_shard():
+                self._run_resident_epoch()
+                return
         for source, targets in self.train_data:
             # host batches go in as they come: the eager path moves them (ref:multigpu.py:48-50), the replayed
             # path stages them itself
