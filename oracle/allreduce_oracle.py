@@ -107,3 +107,34 @@ def ddp_average(per_rank_grads: Sequence[Sequence[np.ndarray]], dtype: str = "f3
     scale = float(np.float32(1.0) / np.float32(ws))
     flat = [flatten_scale([np.ravel(g) for g in grads], offs, total, scale, dtype) for grads in per_rank_grads]
     return unflatten(allreduce_sum(flat, dtype), offs, lengths)
+
+
+# ---- round 2: the two optional arithmetic extras of the C ABI ------------------------------------------------
+def allreduce_sum_scaled(buckets: Sequence[np.ndarray], dtype: str, scale: float) -> np.ndarray:
+    """``b200ddp_allreduce(..., scale)``: the rank-ordered fp32 sum multiplied by fl32(scale) BEFORE the one
+    rounding to the storage type — what the comm-hook shim uses, since torch hands a hook an UNdivided bucket
+    (torch:nn/parallel/distributed.py:2021-2023; the default path divides first, default_comm_hooks.hpp:36-41).
+    ``scale == 1`` is a bit-exact pass-through of the sum."""
+    acc = to_f32(buckets[0], dtype).astype(np.float32, copy=True)
+    for b in buckets[1:]:
+        acc = (acc + to_f32(b, dtype)).astype(np.float32)
+    s = np.float32(scale)
+    if s == np.float32(1.0):
+        return from_f32(acc, dtype)
+    if dtype == "f32":
+        return (acc * s).astype(np.float32)
+    # 16-bit storage: the kernels round the sum to the storage type, then scale in fp32 and round again
+    # (scale_vec on the packed vector): two roundings, restated literally
+    summed = to_f32(from_f32(acc, dtype), dtype)
+    return from_f32((summed * s).astype(np.float32), dtype)
+
+
+def sgd_epilogue(param: np.ndarray, grad: np.ndarray, lr: float, dtype: str = "f32") -> np.ndarray:
+    """The opt-in optimizer epilogue (``b200ddp_unflatten_sgd`` / ``b200ddp_fused_bucket_sgd``): plain SGD as
+    ``torch.optim.SGD(lr)`` without momentum / weight decay applies it, ``param.add_(grad, alpha=-lr)``
+    (ref:multigpu.py:43,68), computed as ONE fused multiply-add in fp32 and rounded once to the storage type:
+    p <- fma(-lr, g, p).  The fma is restated in float64 (the product of two fp32 values is exact there)."""
+    p64 = to_f32(param, dtype).astype(np.float64)
+    g64 = to_f32(grad, dtype).astype(np.float64)
+    exact = np.float64(np.float32(-lr)) * g64 + p64  # product exact, one float64 rounding on the sum
+    return from_f32(exact.astype(np.float32), dtype)

@@ -142,3 +142,44 @@ def test_bf16_average_rounds_once():
     exact = np.sum(np.stack(scaled).astype(np.float64), axis=0)
     got = ao.bf16_bits_to_f32(out).astype(np.float64)
     assert np.max(np.abs(got - exact) / np.maximum(np.abs(exact), 1e-3)) < 2 ** -7
+
+
+def test_round2_oracle_extras_are_pinned_against_torch():
+    """`scale` of the allreduce and the optimizer epilogue, restated in the oracle, against torch on CPU: the scaled
+    sum is the rank-ordered fp32 sum times fl32(scale); the epilogue is torch.optim.SGD's `param.add_(grad, alpha=-lr)`
+    within one fp32 ulp (torch's CPU kernel may or may not contract the multiply-add), bf16 within one bf16 ulp."""
+    import numpy as np
+    import torch
+
+    from oracle import allreduce_oracle as ao
+
+    rng = np.random.default_rng(7)
+    bufs = [rng.uniform(-1, 1, 4099).astype(np.float32) for _ in range(5)]
+    plain = ao.allreduce_sum(bufs, "f32")
+    assert np.array_equal(ao.allreduce_sum_scaled(bufs, "f32", 1.0), plain)
+    assert np.array_equal(ao.allreduce_sum_scaled(bufs, "f32", 0.2), plain * np.float32(0.2))
+    acc = torch.zeros(4099)
+    acc.copy_(torch.from_numpy(bufs[0]))
+    for b in bufs[1:]:
+        acc = acc + torch.from_numpy(b)
+    assert np.array_equal((acc * 0.2).numpy(), ao.allreduce_sum_scaled(bufs, "f32", 0.2))
+
+    p = torch.from_numpy(rng.uniform(-1, 1, 4099).astype(np.float32))
+    g = torch.from_numpy(rng.uniform(-1, 1, 4099).astype(np.float32))
+    param = torch.nn.Parameter(p.clone())
+    param.grad = g.clone()
+    torch.optim.SGD([param], lr=0.0375).step()
+    want = param.detach().numpy()
+    got = ao.sgd_epilogue(p.numpy(), g.numpy(), 0.0375)
+    ulp = np.spacing(np.abs(want).astype(np.float32))
+    assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= ulp)
+    # bf16 storage
+    pb, gb = p.bfloat16(), g.bfloat16()
+    param = torch.nn.Parameter(pb.clone())
+    param.grad = gb.clone()
+    torch.optim.SGD([param], lr=0.0375).step()
+    bits = lambda t: t.view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+    got = ao.bf16_bits_to_f32(ao.sgd_epilogue(bits(pb), bits(gb), 0.0375, "bf16"))
+    want = param.detach().float().numpy()
+    scale = np.maximum(np.abs(want), np.abs(pb.float().numpy()))  # a result near zero is a cancellation: one ulp of p
+    assert np.all(np.abs(got - want) <= scale * 2.0 ** -7 + 1e-30)
