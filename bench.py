@@ -925,8 +925,9 @@ def main_b200(args):
         launches = (comm.launch_count - n0) * blocks
 
     # ---- nvlink peak (N>1) ---------------------------------------------------------------------------------------
-    nvl_peak, nvl_src = NVLINK_NOMINAL, ("nominal NVLink 5: 900 GB/s per direction per GPU (pool guide: measured peer "
-                                         "copy 770 GB/s)")
+    nvl_peak, nvl_src = NVLINK_NOMINAL, (f"nominal NVLink 5: {NVLINK_NOMINAL:.0f} GB/s per direction per GPU (pool guide: "
+                                         f"measured peer copy {NVLINK_POOL_MEASURED:.0f} GB/s; this run's own peer-read "
+                                         "rate is in nvlink_peak_measured)")
     nvlink = None
     side_comm = None
     if world > 1:
